@@ -1,0 +1,172 @@
+// obstacle_world.h -- host-side obstacle preprocessing for the batched ORCA simulator.
+//
+// Replaces RVOSimulator::addObstacle + processObstacles (reference call sites
+// collision_avoidence_env.py:118-123,145 ; ALAN_true.py:196-210,476), SURVEY.md A.1/A.3:
+// polygons -> linked vertex ring (point, unit direction, convexity) -> BSP over the edges,
+// splitting straddling edges and appending the new vertices.  It runs once per world on the
+// host; the flat tables it produces are what the kernels traverse (orca_core.cuh).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+namespace orca_host {
+
+struct ObstacleTables {
+  // per vertex (an edge is identified by its first vertex)
+  std::vector<float> px, py, ux, uy;
+  std::vector<int32_t> next, prev;
+  std::vector<uint8_t> convex;
+  // BSP nodes; node 0 is the root when non-empty
+  std::vector<int32_t> node_vertex, node_left, node_right;
+  int depth = 0;
+
+  int num_vertices() const { return static_cast<int>(px.size()); }
+  int num_nodes() const { return static_cast<int>(node_vertex.size()); }
+};
+
+namespace detail {
+
+constexpr float kEps = 0.00001f;
+
+inline float det2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
+// leftOf(a, b, c) = det(a - c, b - a)
+inline float left_of(float ax, float ay, float bx, float by, float cx, float cy) {
+  return det2(ax - cx, ay - cy, bx - ax, by - ay);
+}
+
+struct Builder {
+  ObstacleTables& T;
+  explicit Builder(ObstacleTables& t) : T(t) {}
+
+  using Rank = std::pair<size_t, size_t>;
+  static Rank rank(size_t l, size_t r) { return {l > r ? l : r, l > r ? r : l}; }
+
+  void classify(int ei, int ej, float* a, float* b) const {
+    const int i2 = T.next[ei], j2 = T.next[ej];
+    *a = left_of(T.px[ei], T.py[ei], T.px[i2], T.py[i2], T.px[ej], T.py[ej]);
+    *b = left_of(T.px[ei], T.py[ei], T.px[i2], T.py[i2], T.px[j2], T.py[j2]);
+  }
+
+  int build(const std::vector<int>& edges, int level) {
+    if (edges.empty()) return -1;
+    if (level + 1 > T.depth) T.depth = level + 1;
+    const size_t n = edges.size();
+    size_t best = 0;
+    Rank best_rank = rank(n, n);
+    size_t best_l = n, best_r = n;
+    for (size_t i = 0; i < n; ++i) {
+      size_t nl = 0, nr = 0;
+      for (size_t j = 0; j < n; ++j) {
+        if (i == j) continue;
+        float a, b;
+        classify(edges[i], edges[j], &a, &b);
+        if (a >= -kEps && b >= -kEps) {
+          ++nl;
+        } else if (a <= kEps && b <= kEps) {
+          ++nr;
+        } else {
+          ++nl;
+          ++nr;
+        }
+        if (rank(nl, nr) >= best_rank) break;
+      }
+      if (rank(nl, nr) < best_rank) {
+        best_rank = rank(nl, nr);
+        best_l = nl;
+        best_r = nr;
+        best = i;
+      }
+    }
+    std::vector<int> lefts, rights;
+    lefts.reserve(best_l);
+    rights.reserve(best_r);
+    const int ei = edges[best];
+    for (size_t j = 0; j < n; ++j) {
+      if (j == best) continue;
+      const int ej = edges[j];
+      float a, b;
+      classify(ei, ej, &a, &b);
+      if (a >= -kEps && b >= -kEps) {
+        lefts.push_back(ej);
+      } else if (a <= kEps && b <= kEps) {
+        rights.push_back(ej);
+      } else {
+        // split edge ej where the supporting line of ei crosses it
+        const int i2 = T.next[ei], j2 = T.next[ej];
+        const float ix = T.px[i2] - T.px[ei], iy = T.py[i2] - T.py[ei];
+        const float t = det2(ix, iy, T.px[ej] - T.px[ei], T.py[ej] - T.py[ei]) /
+                        det2(ix, iy, T.px[ej] - T.px[j2], T.py[ej] - T.py[j2]);
+        const float sx = T.px[ej] + t * (T.px[j2] - T.px[ej]);
+        const float sy = T.py[ej] + t * (T.py[j2] - T.py[ej]);
+        const int nid = T.num_vertices();
+        T.px.push_back(sx);
+        T.py.push_back(sy);
+        T.ux.push_back(T.ux[ej]);
+        T.uy.push_back(T.uy[ej]);
+        T.next.push_back(j2);
+        T.prev.push_back(ej);
+        T.convex.push_back(1);
+        T.next[ej] = nid;
+        T.prev[j2] = nid;
+        if (a > 0.f) {
+          lefts.push_back(ej);
+          rights.push_back(nid);
+        } else {
+          rights.push_back(ej);
+          lefts.push_back(nid);
+        }
+      }
+    }
+    const int me = T.num_nodes();
+    T.node_vertex.push_back(ei);
+    T.node_left.push_back(-1);
+    T.node_right.push_back(-1);
+    const int l = build(lefts, level + 1);
+    const int r = build(rights, level + 1);
+    T.node_left[me] = l;
+    T.node_right[me] = r;
+    return me;
+  }
+};
+
+}  // namespace detail
+
+// Appends one polygon (>= 2 vertices) as a closed ring; returns the id of its first vertex or -1.
+inline int add_polygon(ObstacleTables& T, const float* xy, int n) {
+  if (n < 2) return -1;
+  const int first = T.num_vertices();
+  for (int i = 0; i < n; ++i) {
+    const int nx = (i == n - 1) ? 0 : i + 1;
+    const int pv = (i == 0) ? n - 1 : i - 1;
+    const float dx = xy[2 * nx] - xy[2 * i], dy = xy[2 * nx + 1] - xy[2 * i + 1];
+    const float inv = 1.0f / std::sqrt(dx * dx + dy * dy);
+    T.px.push_back(xy[2 * i]);
+    T.py.push_back(xy[2 * i + 1]);
+    T.ux.push_back(dx * inv);
+    T.uy.push_back(dy * inv);
+    T.next.push_back(first + nx);
+    T.prev.push_back(first + pv);
+    bool cvx = true;
+    if (n != 2) {
+      cvx = detail::left_of(xy[2 * pv], xy[2 * pv + 1], xy[2 * i], xy[2 * i + 1], xy[2 * nx], xy[2 * nx + 1]) >= 0.f;
+    }
+    T.convex.push_back(cvx ? 1 : 0);
+  }
+  return first;
+}
+
+// processObstacles: build the BSP over every edge added so far.
+inline void process(ObstacleTables& T) {
+  T.node_vertex.clear();
+  T.node_left.clear();
+  T.node_right.clear();
+  T.depth = 0;
+  std::vector<int> all(static_cast<size_t>(T.num_vertices()));
+  for (size_t i = 0; i < all.size(); ++i) all[i] = static_cast<int>(i);
+  detail::Builder(T).build(all, 0);
+}
+
+}  // namespace orca_host

@@ -1,0 +1,451 @@
+// orca_api.cu -- C ABI (include/orca_b200.h) over the sm_100a kernels.
+//
+// Build (see collision_avoidance_b200/build.py):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
+//        -Xcompiler -fPIC,-ffp-contract=off -shared -o liborca_b200.so orca_api.cu
+// -fmad=false is part of the contract: see orca_core.cuh.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/orca_b200.h"
+#include "obstacle_world.h"
+#include "orca_core.cuh"
+#include "orca_grid.cuh"
+#include "orca_step_small.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) return fail(ORCA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+}  // namespace
+
+struct OrcaSim {
+  OrcaParams p{};
+  int device = 0;
+  int E = 0, N = 0;
+  // obstacle world(s)
+  std::vector<orca_host::ObstacleTables> worlds;  // 1 (shared) or E
+  bool per_env = false;
+  float4* d_vert_pd = nullptr;
+  int4* d_vert_link = nullptr;
+  int4* d_bsp = nullptr;
+  int* d_env_nodes = nullptr;
+  int shared_nodes = 0;
+  int vert_stride = 0;
+  // staging for the *_host entry points
+  float2* d_pos = nullptr;
+  float2* d_vel = nullptr;
+  float2* d_aux = nullptr;
+  cudaStream_t host_stream = nullptr;
+  // uniform-grid scratch (large worlds)
+  orca::GridScratch grid;
+  int64_t launches = 0;
+};
+
+namespace {
+
+void free_obstacles(OrcaSim* s) {
+  cudaFree(s->d_vert_pd);
+  cudaFree(s->d_vert_link);
+  cudaFree(s->d_bsp);
+  cudaFree(s->d_env_nodes);
+  s->d_vert_pd = nullptr;
+  s->d_vert_link = nullptr;
+  s->d_bsp = nullptr;
+  s->d_env_nodes = nullptr;
+  s->shared_nodes = 0;
+  s->vert_stride = 0;
+  s->worlds.clear();
+}
+
+int pick_k(int k) {
+  if (k <= 5) return 5;
+  if (k <= 10) return 10;
+  if (k <= 16) return 16;
+  return -1;
+}
+
+void fill_common(const OrcaSim* s, orca::StepArgs* a) {
+  std::memset(a, 0, sizeof(*a));
+  a->E = s->E;
+  a->N = s->N;
+  a->k = s->p.max_neighbors;
+  a->dt = s->p.time_step;
+  a->inv_dt = 1.0f / s->p.time_step;
+  a->nd_sq = s->p.neighbor_dist * s->p.neighbor_dist;
+  a->inv_th = 1.0f / s->p.time_horizon;
+  a->inv_tho = 1.0f / s->p.time_horizon_obst;
+  a->radius = s->p.radius;
+  a->vmax = s->p.max_speed;
+  const float orange = s->p.time_horizon_obst * s->p.max_speed + s->p.radius;
+  a->obst_range_sq = orange * orange;
+  a->vert_pd = s->d_vert_pd;
+  a->vert_link = s->d_vert_link;
+  a->bsp = s->d_bsp;
+  a->env_nodes = s->per_env ? s->d_env_nodes : nullptr;
+  a->shared_nodes = s->shared_nodes;
+  a->vert_stride = s->per_env ? s->vert_stride : 0;
+}
+
+template <int K, int POLICY>
+int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
+  const int N = s->N;
+  const int tpb = (N <= 128) ? 128 : 256;
+  orca::StepArgs args = a;
+  args.envs_per_block = tpb / N;
+  const int blocks = (s->E + args.envs_per_block - 1) / args.envs_per_block;
+  const size_t smem = (size_t)tpb * (16 + (size_t)(K + ORCA_MAX_OBST_LINES) * 16);
+  auto kern = orca::step_small_kernel<K, POLICY>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * (16 + (K + ORCA_MAX_OBST_LINES) * 16)));
+    attr_set = true;
+  }
+  kern<<<blocks, tpb, smem, st>>>(args);
+  CUDA_TRY(cudaGetLastError());
+  s->launches += 1;
+  return ORCA_OK;
+}
+
+template <int K>
+int launch_small_k(OrcaSim* s, const orca::StepArgs& a, int policy, cudaStream_t st) {
+  switch (policy) {
+    case ORCA_POLICY_EXTERNAL:
+      return launch_small_kp<K, orca::POLICY_EXTERNAL>(s, a, st);
+    case ORCA_POLICY_GOAL:
+      return launch_small_kp<K, orca::POLICY_GOAL>(s, a, st);
+    case ORCA_POLICY_RL:
+      return launch_small_kp<K, orca::POLICY_RL>(s, a, st);
+    case ORCA_POLICY_ALAN:
+      return launch_small_kp<K, orca::POLICY_ALAN>(s, a, st);
+    default:
+      return fail(ORCA_ERR_INVALID, "unknown policy %d", policy);
+  }
+}
+
+int launch_step(OrcaSim* s, const orca::StepArgs& a, int policy, cudaStream_t st) {
+  if (s->N > 256) {
+    return orca::launch_grid_step(s->grid, a, policy, st, &s->launches, &g_last_error);
+  }
+  switch (pick_k(s->p.max_neighbors)) {
+    case 5:
+      return launch_small_k<5>(s, a, policy, st);
+    case 10:
+      return launch_small_k<10>(s, a, policy, st);
+    case 16:
+      return launch_small_k<16>(s, a, policy, st);
+    default:
+      return fail(ORCA_ERR_UNSUPPORTED, "max_neighbors=%d > 16 is not supported", s->p.max_neighbors);
+  }
+}
+
+int ensure_host_staging(OrcaSim* s) {
+  if (s->d_pos != nullptr) return ORCA_OK;
+  const size_t bytes = (size_t)s->E * s->N * sizeof(float2);
+  CUDA_TRY(cudaMalloc(&s->d_pos, bytes));
+  CUDA_TRY(cudaMalloc(&s->d_vel, bytes));
+  CUDA_TRY(cudaMalloc(&s->d_aux, bytes));
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->host_stream, cudaStreamNonBlocking));
+  return ORCA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orca_abi_version(void) { return ORCA_B200_ABI_VERSION; }
+const char* orca_last_error(void) { return g_last_error.c_str(); }
+
+int orca_create(const OrcaParams* params, int device, int num_envs, int agents_per_env, OrcaSim** out) {
+  if (params == nullptr || out == nullptr) return fail(ORCA_ERR_INVALID, "null argument");
+  if (num_envs <= 0 || agents_per_env <= 0) return fail(ORCA_ERR_INVALID, "num_envs and agents_per_env must be > 0");
+  if ((long long)num_envs * agents_per_env > (1ll << 30)) return fail(ORCA_ERR_UNSUPPORTED, "more than 2^30 agents");
+  if (!(params->time_step > 0.f) || !(params->time_horizon > 0.f) || !(params->time_horizon_obst > 0.f))
+    return fail(ORCA_ERR_INVALID, "time_step / time_horizon / time_horizon_obst must be > 0");
+  if (params->max_neighbors < 0) return fail(ORCA_ERR_INVALID, "max_neighbors must be >= 0");
+  if (pick_k(params->max_neighbors) < 0)
+    return fail(ORCA_ERR_UNSUPPORTED, "max_neighbors=%d > 16 is not supported", params->max_neighbors);
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(ORCA_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  OrcaSim* s = new OrcaSim();
+  s->p = *params;
+  s->device = device;
+  s->E = num_envs;
+  s->N = agents_per_env;
+  *out = s;
+  return ORCA_OK;
+}
+
+int orca_destroy(OrcaSim* s) {
+  if (s == nullptr) return ORCA_OK;
+  cudaSetDevice(s->device);
+  free_obstacles(s);
+  cudaFree(s->d_pos);
+  cudaFree(s->d_vel);
+  cudaFree(s->d_aux);
+  if (s->host_stream) cudaStreamDestroy(s->host_stream);
+  orca::grid_free(s->grid);
+  delete s;
+  return ORCA_OK;
+}
+
+int orca_get_params(const OrcaSim* s, OrcaParams* out, int* num_envs, int* agents_per_env) {
+  if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (out) *out = s->p;
+  if (num_envs) *num_envs = s->E;
+  if (agents_per_env) *agents_per_env = s->N;
+  return ORCA_OK;
+}
+
+int orca_set_obstacles(OrcaSim* s, const float* xy, const int32_t* poly_sizes, int num_polys,
+                       const int32_t* polys_per_env) {
+  if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (num_polys < 0 || (num_polys > 0 && (xy == nullptr || poly_sizes == nullptr)))
+    return fail(ORCA_ERR_INVALID, "bad polygon arguments");
+  CUDA_TRY(cudaSetDevice(s->device));
+  free_obstacles(s);
+  s->per_env = (polys_per_env != nullptr);
+  const int n_worlds = s->per_env ? s->E : 1;
+  s->worlds.resize((size_t)n_worlds);
+  int poly = 0;
+  size_t off = 0;
+  for (int w = 0; w < n_worlds; ++w) {
+    const int np = s->per_env ? polys_per_env[w] : num_polys;
+    if (np < 0 || poly + np > num_polys) return fail(ORCA_ERR_INVALID, "polys_per_env does not match num_polys");
+    for (int q = 0; q < np; ++q, ++poly) {
+      if (orca_host::add_polygon(s->worlds[(size_t)w], xy + 2 * off, poly_sizes[poly]) < 0) {
+        free_obstacles(s);
+        return fail(ORCA_ERR_INVALID, "polygon %d has fewer than 2 vertices", poly);
+      }
+      off += (size_t)poly_sizes[poly];
+    }
+    orca_host::process(s->worlds[(size_t)w]);
+    if (s->worlds[(size_t)w].depth > ORCA_MAX_BSP_DEPTH - 1) {
+      free_obstacles(s);
+      return fail(ORCA_ERR_UNSUPPORTED, "obstacle BSP depth %d exceeds %d", s->worlds[(size_t)w].depth,
+                  ORCA_MAX_BSP_DEPTH - 1);
+    }
+  }
+  if (poly != num_polys) return fail(ORCA_ERR_INVALID, "polys_per_env does not cover all polygons");
+  int stride = 0;
+  for (const auto& T : s->worlds) stride = T.num_vertices() > stride ? T.num_vertices() : stride;
+  if (stride == 0) return ORCA_OK;  // no obstacles at all
+  std::vector<float4> pd((size_t)n_worlds * stride);
+  std::vector<int4> link((size_t)n_worlds * stride), bsp((size_t)n_worlds * stride);
+  std::vector<int> nodes((size_t)n_worlds);
+  for (int w = 0; w < n_worlds; ++w) {
+    const auto& T = s->worlds[(size_t)w];
+    nodes[(size_t)w] = T.num_nodes();
+    for (int v = 0; v < stride; ++v) {
+      const size_t o = (size_t)w * stride + v;
+      if (v < T.num_vertices()) {
+        pd[o] = make_float4(T.px[v], T.py[v], T.ux[v], T.uy[v]);
+        link[o] = make_int4(T.next[v], T.prev[v], T.convex[v], 0);
+      } else {
+        pd[o] = make_float4(0, 0, 1, 0);
+        link[o] = make_int4(0, 0, 0, 0);
+      }
+      if (v < T.num_nodes())
+        bsp[o] = make_int4(T.node_vertex[v], T.node_left[v], T.node_right[v], 0);
+      else
+        bsp[o] = make_int4(0, -1, -1, 0);
+    }
+  }
+  CUDA_TRY(cudaMalloc(&s->d_vert_pd, pd.size() * sizeof(float4)));
+  CUDA_TRY(cudaMalloc(&s->d_vert_link, link.size() * sizeof(int4)));
+  CUDA_TRY(cudaMalloc(&s->d_bsp, bsp.size() * sizeof(int4)));
+  CUDA_TRY(cudaMemcpy(s->d_vert_pd, pd.data(), pd.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(s->d_vert_link, link.data(), link.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(s->d_bsp, bsp.data(), bsp.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if (s->per_env) {
+    CUDA_TRY(cudaMalloc(&s->d_env_nodes, nodes.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(s->d_env_nodes, nodes.data(), nodes.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  s->shared_nodes = s->per_env ? 0 : nodes[0];
+  s->vert_stride = stride;
+  return ORCA_OK;
+}
+
+int orca_obstacle_vertex_count(const OrcaSim* s, int env) {
+  if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (s->worlds.empty()) return 0;
+  const size_t w = s->per_env ? (size_t)env : 0;
+  if (w >= s->worlds.size()) return fail(ORCA_ERR_INVALID, "env %d out of range", env);
+  return s->worlds[w].num_vertices();
+}
+
+int orca_get_obstacle_vertices(const OrcaSim* s, int env, float* xy_out, int32_t* next_out, int32_t* prev_out,
+                               int32_t* convex_out) {
+  if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (s->worlds.empty()) return ORCA_OK;
+  const size_t w = s->per_env ? (size_t)env : 0;
+  if (w >= s->worlds.size()) return fail(ORCA_ERR_INVALID, "env %d out of range", env);
+  const auto& T = s->worlds[w];
+  for (int v = 0; v < T.num_vertices(); ++v) {
+    if (xy_out) {
+      xy_out[2 * v] = T.px[(size_t)v];
+      xy_out[2 * v + 1] = T.py[(size_t)v];
+    }
+    if (next_out) next_out[v] = T.next[(size_t)v];
+    if (prev_out) prev_out[v] = T.prev[(size_t)v];
+    if (convex_out) convex_out[v] = T.convex[(size_t)v];
+  }
+  return ORCA_OK;
+}
+
+int orca_step(OrcaSim* s, float* pos_dev, float* vel_dev, const float* pref_dev, void* stream) {
+  if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (pos_dev == nullptr || vel_dev == nullptr || pref_dev == nullptr) return fail(ORCA_ERR_INVALID, "null state pointer");
+  CUDA_TRY(cudaSetDevice(s->device));
+  orca::StepArgs a;
+  fill_common(s, &a);
+  a.pos = reinterpret_cast<float2*>(pos_dev);
+  a.vel = reinterpret_cast<float2*>(vel_dev);
+  a.pref = reinterpret_cast<const float2*>(pref_dev);
+  return launch_step(s, a, ORCA_POLICY_EXTERNAL, static_cast<cudaStream_t>(stream));
+}
+
+int orca_env_step(OrcaSim* s, const OrcaEnvStepArgs* in, void* stream) {
+  if (s == nullptr || in == nullptr) return fail(ORCA_ERR_INVALID, "null argument");
+  if (in->struct_size != sizeof(OrcaEnvStepArgs))
+    return fail(ORCA_ERR_INVALID, "OrcaEnvStepArgs size mismatch (%u vs %zu): ABI skew", in->struct_size,
+                sizeof(OrcaEnvStepArgs));
+  if (in->pos_dev == nullptr || in->vel_dev == nullptr) return fail(ORCA_ERR_INVALID, "pos_dev / vel_dev required");
+  if (in->policy == ORCA_POLICY_EXTERNAL && in->pref_dev == nullptr)
+    return fail(ORCA_ERR_INVALID, "EXTERNAL policy needs pref_dev");
+  if (in->policy != ORCA_POLICY_EXTERNAL && in->goal_dev == nullptr)
+    return fail(ORCA_ERR_INVALID, "goal-directed policies need goal_dev");
+  if (in->policy == ORCA_POLICY_RL && in->action_theta_dev == nullptr)
+    return fail(ORCA_ERR_INVALID, "RL policy needs action_theta_dev");
+  if (in->policy == ORCA_POLICY_ALAN) {
+    if (in->alan_weights_dev == nullptr || in->alan_actions_dev == nullptr)
+      return fail(ORCA_ERR_INVALID, "ALAN policy needs alan_weights_dev and alan_actions_dev");
+    if (in->alan_num_actions < 1 || in->alan_num_actions > ORCA_MAX_ACTIONS)
+      return fail(ORCA_ERR_UNSUPPORTED, "alan_num_actions must be in [1, %d]", ORCA_MAX_ACTIONS);
+    if (!(in->alan_temp > 0.f)) return fail(ORCA_ERR_INVALID, "alan_temp must be > 0");
+  }
+  if (in->done_mode != ORCA_DONE_NONE) {
+    if (in->agent_done_dev == nullptr) return fail(ORCA_ERR_INVALID, "done_mode needs agent_done_dev");
+    if (in->goal_dev == nullptr) return fail(ORCA_ERR_INVALID, "done_mode needs goal_dev");
+  }
+  if (in->nbr_idx_dev != nullptr && in->nbr_cnt_dev == nullptr) return fail(ORCA_ERR_INVALID, "nbr_idx_dev needs nbr_cnt_dev");
+  if (in->obst_nbr_idx_dev != nullptr && in->obst_nbr_cnt_dev == nullptr)
+    return fail(ORCA_ERR_INVALID, "obst_nbr_idx_dev needs obst_nbr_cnt_dev");
+  CUDA_TRY(cudaSetDevice(s->device));
+  orca::StepArgs a;
+  fill_common(s, &a);
+  a.pos = reinterpret_cast<float2*>(in->pos_dev);
+  a.vel = reinterpret_cast<float2*>(in->vel_dev);
+  a.pref = reinterpret_cast<const float2*>(in->pref_dev);
+  a.goal = reinterpret_cast<float2*>(in->goal_dev);
+  a.goal2 = reinterpret_cast<const float2*>(in->goal2_dev);
+  a.action_theta = in->action_theta_dev;
+  a.rl_scale = in->rl_reward_scale;
+  a.done_x = in->done_x_threshold;
+  a.alan_w = in->alan_weights_dev;
+  a.alan_actions = reinterpret_cast<const float2*>(in->alan_actions_dev);
+  a.alan_action_out = in->alan_action_out_dev;
+  a.alan_uniform_in = in->alan_uniform_in_dev;
+  a.A = in->alan_num_actions;
+  a.alan_window = in->alan_window_steps;
+  a.alan_gamma = in->alan_gamma;
+  a.alan_inv_temp = (in->policy == ORCA_POLICY_ALAN) ? 1.0f / in->alan_temp : 0.f;
+  a.seed = in->rng_seed;
+  a.reward = in->reward_dev;
+  a.done = in->agent_done_dev;
+  a.arrival = in->arrival_time_dev;
+  a.env_step = in->env_step_dev;
+  a.env_done_cnt = in->env_done_cnt_dev;
+  a.done_mode = in->done_mode;
+  a.nbr_idx = in->nbr_idx_dev;
+  a.nbr_cnt = in->nbr_cnt_dev;
+  a.onbr_idx = in->obst_nbr_idx_dev;
+  a.onbr_cnt = in->obst_nbr_cnt_dev;
+  a.stats = reinterpret_cast<unsigned long long*>(in->stats_dev);
+  return launch_step(s, a, in->policy, static_cast<cudaStream_t>(stream));
+}
+
+int orca_neighbors(OrcaSim* s, const float* pos_dev, int32_t* nbr_idx_dev, float* nbr_distsq_dev, int32_t* nbr_cnt_dev,
+                   int32_t* obst_nbr_idx_dev, int32_t* obst_nbr_cnt_dev, void* stream) {
+  if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (pos_dev == nullptr || nbr_idx_dev == nullptr || nbr_cnt_dev == nullptr)
+    return fail(ORCA_ERR_INVALID, "pos_dev, nbr_idx_dev and nbr_cnt_dev are required");
+  if (obst_nbr_idx_dev != nullptr && obst_nbr_cnt_dev == nullptr) return fail(ORCA_ERR_INVALID, "obst_nbr_idx_dev needs obst_nbr_cnt_dev");
+  CUDA_TRY(cudaSetDevice(s->device));
+  orca::StepArgs a;
+  fill_common(s, &a);
+  // the search only reads positions; velocities alias them and nothing is written back
+  a.pos = reinterpret_cast<float2*>(const_cast<float*>(pos_dev));
+  a.vel = a.pos;
+  a.pref = a.pos;
+  a.nbr_idx = nbr_idx_dev;
+  a.nbr_dsq = nbr_distsq_dev;
+  a.nbr_cnt = nbr_cnt_dev;
+  a.onbr_idx = obst_nbr_idx_dev;
+  a.onbr_cnt = obst_nbr_cnt_dev;
+  a.neighbors_only = 1;
+  return launch_step(s, a, ORCA_POLICY_EXTERNAL, static_cast<cudaStream_t>(stream));
+}
+
+int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pref_or_goal_host, int policy,
+                   int upload_state, int steps) {
+  if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (pos_host == nullptr || vel_host == nullptr || pref_or_goal_host == nullptr)
+    return fail(ORCA_ERR_INVALID, "null host buffer");
+  if (policy != ORCA_POLICY_EXTERNAL && policy != ORCA_POLICY_GOAL)
+    return fail(ORCA_ERR_INVALID, "orca_step_host supports the EXTERNAL and GOAL policies");
+  if (steps < 1) return fail(ORCA_ERR_INVALID, "steps must be >= 1");
+  CUDA_TRY(cudaSetDevice(s->device));
+  int rc = ensure_host_staging(s);
+  if (rc != ORCA_OK) return rc;
+  const size_t bytes = (size_t)s->E * s->N * sizeof(float2);
+  cudaStream_t st = s->host_stream;
+  if (upload_state) {
+    CUDA_TRY(cudaMemcpyAsync(s->d_pos, pos_host, bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_vel, vel_host, bytes, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaMemcpyAsync(s->d_aux, pref_or_goal_host, bytes, cudaMemcpyHostToDevice, st));
+  orca::StepArgs a;
+  fill_common(s, &a);
+  a.pos = s->d_pos;
+  a.vel = s->d_vel;
+  if (policy == ORCA_POLICY_EXTERNAL)
+    a.pref = s->d_aux;
+  else
+    a.goal = s->d_aux;
+  for (int t = 0; t < steps; ++t) {
+    rc = launch_step(s, a, policy, st);
+    if (rc != ORCA_OK) return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(pos_host, s->d_pos, bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(vel_host, s->d_vel, bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return ORCA_OK;
+}
+
+int64_t orca_launch_count(const OrcaSim* s) { return s ? s->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,578 @@
+// orca_core.cuh -- per-agent ORCA arithmetic shared by every kernel of the library.
+//
+// Computes what one RVO2 agent does inside doStep (reference call sites:
+// collision_avoidence_env.py:385,448 and ALAN_true.py:601,632 -> RVO2
+// Agent::computeNeighbors / computeNewVelocity / linearProgram1-3):
+//   * obstacle-neighbor query over the processed obstacle BSP,
+//   * ORCA half-planes for obstacle edges and for agent neighbors,
+//   * the incremental 2-D linear programs LP1/LP2/LP3.
+//
+// Everything is float32 with one rounding per operation: the translation unit is built
+// with -fmad=false (no FMA contraction) and IEEE sqrt/div, so on identical inputs the
+// results are bit-identical to a scalar x86 evaluation of the same expressions.
+//
+// The functions are ORCA_HD so tests can also compile them for the host (tests/host_emul)
+// to debug logic without a GPU; the shipped library only ever runs them on the device.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ORCA_HD __host__ __device__ __forceinline__
+#define ORCA_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define ORCA_HD inline
+#define ORCA_HD_NOINLINE inline
+#include "host_vec_types.h"
+#endif
+
+#ifndef ORCA_MAX_OBST_NEIGHBORS
+#define ORCA_MAX_OBST_NEIGHBORS 16
+#endif
+#ifndef ORCA_MAX_OBST_LINES
+#define ORCA_MAX_OBST_LINES 6
+#endif
+#ifndef ORCA_MAX_ACTIONS
+#define ORCA_MAX_ACTIONS 16
+#endif
+#define ORCA_MAX_BSP_DEPTH 64
+
+namespace orca {
+
+constexpr float kEps = 0.00001f;  // RVO_EPSILON
+
+// ---- tiny 2-vector algebra (operation order fixed; see header comment) -----------------
+ORCA_HD float2 v2(float x, float y) {
+  float2 r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+ORCA_HD float2 add(float2 a, float2 b) { return v2(a.x + b.x, a.y + b.y); }
+ORCA_HD float2 sub(float2 a, float2 b) { return v2(a.x - b.x, a.y - b.y); }
+ORCA_HD float2 neg(float2 a) { return v2(-a.x, -a.y); }
+ORCA_HD float2 mul(float s, float2 a) { return v2(s * a.x, s * a.y); }
+ORCA_HD float dot(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
+ORCA_HD float det(float2 a, float2 b) { return a.x * b.y - a.y * b.x; }
+ORCA_HD float abs_sq(float2 a) { return a.x * a.x + a.y * a.y; }
+ORCA_HD float sqr(float s) { return s * s; }
+// vector / scalar is "multiply by reciprocal" in RVO2 (SURVEY Appendix A helpers)
+ORCA_HD float2 div_s(float2 a, float s) {
+  const float inv = 1.0f / s;
+  return v2(a.x * inv, a.y * inv);
+}
+ORCA_HD float2 unit(float2 a) { return div_s(a, sqrtf(abs_sq(a))); }
+ORCA_HD float left_of(float2 a, float2 b, float2 c) { return det(sub(a, c), sub(b, a)); }
+ORCA_HD float fmin_first(float a, float b) { return (b < a) ? b : a; }  // std::min(a, b)
+ORCA_HD float fmax_first(float a, float b) { return (a < b) ? b : a; }  // std::max(a, b)
+
+ORCA_HD float dist_sq_point_segment(float2 a, float2 b, float2 c) {
+  const float2 ab = sub(b, a);
+  const float r = dot(sub(c, a), ab) / abs_sq(ab);
+  if (r < 0.f) return abs_sq(sub(c, a));
+  if (r > 1.f) return abs_sq(sub(c, b));
+  return abs_sq(sub(c, add(a, mul(r, ab))));
+}
+
+// ---- line storage: line i of this agent lives at base[i * stride] ------------------------
+// (point.x, point.y, dir.x, dir.y).  In the kernels `base` points into shared memory with
+// stride = blockDim.x so consecutive lanes hit consecutive 16-byte words (conflict-free).
+struct Lines {
+  float4* base;
+  int stride;
+  ORCA_HD float4 get(int i) const { return base[i * stride]; }
+  ORCA_HD void set(int i, float2 point, float2 dir) const {
+    float4 v;
+    v.x = point.x;
+    v.y = point.y;
+    v.z = dir.x;
+    v.w = dir.y;
+    base[i * stride] = v;
+  }
+};
+ORCA_HD float2 pt(float4 l) { return v2(l.x, l.y); }
+ORCA_HD float2 dr(float4 l) { return v2(l.z, l.w); }
+
+// ---- processed obstacle world of one env ---------------------------------------------------
+// vert_pd[v]   = (point.x, point.y, unitDir.x, unitDir.y)
+// vert_link[v] = (next, prev, isConvex, 0)
+// bsp[n]       = (vertex, left child, right child, 0); node 0 is the root; -1 = no child
+struct ObstacleWorld {
+  const float4* vert_pd;
+  const int4* vert_link;
+  const int4* bsp;
+  int n_nodes;
+};
+
+#if defined(__CUDA_ARCH__)
+#define ORCA_LDG(p) __ldg(p)
+#else
+#define ORCA_LDG(p) (*(p))
+#endif
+
+// ---- linear programs -------------------------------------------------------------
+// LP1: optimise along line i subject to the speed disc and lines [0, i).
+template <class LS>
+ORCA_HD bool lp1(const LS& L, int i, float radius, float2 opt, bool dir_opt, float2& result) {
+  const float4 li = L.get(i);
+  const float2 pi = pt(li), di = dr(li);
+  const float dp = dot(pi, di);
+  const float disc = sqr(dp) + sqr(radius) - abs_sq(pi);
+  if (disc < 0.f) return false;
+  const float sq = sqrtf(disc);
+  float t_lo = -dp - sq;
+  float t_hi = -dp + sq;
+  for (int j = 0; j < i; ++j) {
+    const float4 lj = L.get(j);
+    const float den = det(di, dr(lj));
+    const float num = det(dr(lj), sub(pi, pt(lj)));
+    if (fabsf(den) <= kEps) {
+      if (num < 0.f) return false;
+      continue;
+    }
+    const float t = num / den;
+    if (den >= 0.f)
+      t_hi = fmin_first(t_hi, t);
+    else
+      t_lo = fmax_first(t_lo, t);
+    if (t_lo > t_hi) return false;
+  }
+  float t;
+  if (dir_opt) {
+    t = (dot(opt, di) > 0.f) ? t_hi : t_lo;
+  } else {
+    t = dot(di, sub(opt, pi));
+    if (t < t_lo)
+      t = t_lo;
+    else if (t > t_hi)
+      t = t_hi;
+  }
+  result = add(pi, mul(t, di));
+  return true;
+}
+
+// LP2: returns the index of the first line that cannot be satisfied (n on success).
+// Written as "skip to the next violated line, then run LP1" so that diverged lanes of a
+// warp meet again at every LP1 instead of serialising one LP1 per line index.
+template <class LS>
+ORCA_HD int lp2(const LS& L, int n, float radius, float2 opt, bool dir_opt, float2& result) {
+  if (dir_opt) {
+    result = mul(radius, opt);  // opt * radius
+  } else if (abs_sq(opt) > sqr(radius)) {
+    result = mul(radius, unit(opt));  // normalize(opt) * radius
+  } else {
+    result = opt;
+  }
+  int i = 0;
+  for (;;) {
+    while (i < n) {
+      const float4 li = L.get(i);
+      if (det(dr(li), sub(pt(li), result)) > 0.f) break;
+      ++i;
+    }
+    if (i >= n) return n;
+    const float2 keep = result;
+    if (!lp1(L, i, radius, opt, dir_opt, result)) {
+      result = keep;
+      return i;
+    }
+    ++i;
+  }
+}
+
+// LP3: minimise the maximum violation of the agent lines [n_obst, n), obstacle lines hard.
+// `P` is scratch line storage for the projected programme (at least n entries).
+template <class LS, class PS>
+ORCA_HD void lp3(const LS& L, int n, int n_obst, int begin, float radius, const PS& P, float2& result) {
+  float distance = 0.f;
+  for (int i = begin; i < n; ++i) {
+    const float4 li = L.get(i);
+    const float2 pi = pt(li), di = dr(li);
+    if (det(di, sub(pi, result)) > distance) {
+      int m = 0;
+      for (int j = 0; j < n_obst; ++j) {
+        const float4 lj = L.get(j);
+        P.set(m++, pt(lj), dr(lj));
+      }
+      for (int j = n_obst; j < i; ++j) {
+        const float4 lj = L.get(j);
+        const float2 pj = pt(lj), dj = dr(lj);
+        const float d = det(di, dj);
+        float2 np;
+        if (fabsf(d) <= kEps) {
+          if (dot(di, dj) > 0.f) continue;
+          np = mul(0.5f, add(pi, pj));
+        } else {
+          np = add(pi, mul(det(dj, sub(pi, pj)) / d, di));
+        }
+        P.set(m++, np, unit(sub(dj, di)));
+      }
+      const float2 keep = result;
+      if (lp2(P, m, radius, v2(-di.y, di.x), true, result) < m) result = keep;
+      distance = det(di, sub(pi, result));
+    }
+  }
+}
+
+// ---- agent-agent half-plane (second half) -------------------------------------------
+// cr = r_i + r_j.  Returns the line; *collided is set when distSq <= cr^2 (RVO2's collision branch).
+ORCA_HD float4 agent_line(float2 p, float2 v, float2 po, float2 vo, float cr, float inv_th, float inv_dt,
+                          bool* collided) {
+  const float2 rp = sub(po, p);
+  const float2 rv = sub(v, vo);
+  const float d_sq = abs_sq(rp);
+  const float cr_sq = sqr(cr);
+  const bool apart = d_sq > cr_sq;
+  // cut-off circle of horizon tau when apart, of horizon dt when already overlapping
+  const float inv_t = apart ? inv_th : inv_dt;
+  const float2 w = sub(rv, mul(inv_t, rp));
+  const float w_sq = abs_sq(w);
+  const float dp1 = dot(w, rp);
+  const bool on_circle = !apart || (dp1 < 0.f && sqr(dp1) > cr_sq * w_sq);
+  // both shapes need exactly one sqrt and one reciprocal; select their operands
+  const float root = sqrtf(on_circle ? w_sq : (d_sq - cr_sq));  // |w|  or  leg
+  const float inv = 1.0f / (on_circle ? root : d_sq);
+  float2 dir, u;
+  if (on_circle) {
+    const float2 uw = v2(w.x * inv, w.y * inv);
+    dir = v2(uw.y, -uw.x);
+    u = mul(cr * inv_t - root, uw);
+  } else {
+    const float leg = root;
+    if (det(rp, w) > 0.f) {
+      dir = v2((rp.x * leg - rp.y * cr) * inv, (rp.x * cr + rp.y * leg) * inv);
+    } else {
+      dir = neg(v2((rp.x * leg + rp.y * cr) * inv, (-rp.x * cr + rp.y * leg) * inv));
+    }
+    const float dp2 = dot(rv, dir);
+    u = sub(mul(dp2, dir), rv);
+  }
+  *collided = !apart;
+  const float2 point = add(v, mul(0.5f, u));
+  float4 out;
+  out.x = point.x;
+  out.y = point.y;
+  out.z = dir.x;
+  out.w = dir.y;
+  return out;
+}
+
+// ---- k-nearest list in registers ------------------------------------------------------------------
+// Sorted ascending (distSq, id).  Slots >= k hold -1 so they never accept a candidate; slots < k
+// start at rangeSq, which makes the strict `<` test do double duty as RVO2's range test and its
+// "shrink the range to the k-th best" rule.  Equal distances keep the earlier
+// entry in front (first visited wins); callers visit candidates in ascending agent id.
+template <int K>
+struct NearestK {
+  float d[K];
+  int id[K];
+  float thresh;
+  ORCA_HD void init(int k, float range_sq) {
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      d[s] = (s < k) ? range_sq : -1.0f;
+      id[s] = -1;
+    }
+    thresh = (k > 0) ? range_sq : -1.0f;
+  }
+  ORCA_HD void offer(float cand_d, int cand_id, int k) {
+    if (cand_d < thresh) {
+      float cd = cand_d;
+      int ci = cand_id;
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        const bool sw = cd < d[s];
+        const float td = d[s];
+        const int ti = id[s];
+        d[s] = sw ? cd : td;
+        id[s] = sw ? ci : ti;
+        cd = sw ? td : cd;
+        ci = sw ? ti : ci;
+        if (s == k - 1) thresh = d[s];
+      }
+    }
+  }
+  ORCA_HD int count() const {
+    int c = 0;
+#pragma unroll
+    for (int s = 0; s < K; ++s) c += (id[s] >= 0) ? 1 : 0;
+    return c;
+  }
+};
+
+// ---- obstacle neighbors (SURVEY A.3 query + A.4 insertObstacleNeighbor) -----------------------------
+// Walks the BSP exactly like the recursive query (near side, node, far side if the splitting line
+// is within range) so that equal-distance edges keep RVO2's visiting order.  Result: edge ids
+// (first vertex of the edge) ascending by distance in od/oid, count in *cnt.
+ORCA_HD void obstacle_neighbors(const ObstacleWorld& W, float2 p, float range_sq, float* od, int* oid, int* cnt,
+                                bool* overflow) {
+  int n = 0;
+  if (W.n_nodes > 0) {
+    // explicit stack of (node << 1 | visited-near-side)
+    int stk[ORCA_MAX_BSP_DEPTH];
+    int sp = 0;
+    stk[sp++] = 0;
+    while (sp > 0) {
+      const int top = stk[sp - 1];
+      const int node = top >> 1;
+      const int4 nd = ORCA_LDG(&W.bsp[node]);
+      const int v1 = nd.x;
+      const float4 a = ORCA_LDG(&W.vert_pd[v1]);
+      const int v2i = ORCA_LDG(&W.vert_link[v1]).x;
+      const float4 b = ORCA_LDG(&W.vert_pd[v2i]);
+      const float2 p1 = v2(a.x, a.y), p2 = v2(b.x, b.y);
+      const float side = left_of(p1, p2, p);
+      const int near_c = (side >= 0.f) ? nd.y : nd.z;
+      const int far_c = (side >= 0.f) ? nd.z : nd.y;
+      if ((top & 1) == 0) {
+        stk[sp - 1] = top | 1;
+        if (near_c >= 0 && sp < ORCA_MAX_BSP_DEPTH) stk[sp++] = near_c << 1;
+        continue;
+      }
+      --sp;
+      const float d_line = sqr(side) / abs_sq(sub(p2, p1));
+      if (d_line < range_sq) {
+        if (side < 0.f) {
+          const float d = dist_sq_point_segment(p1, p2, p);
+          if (d < range_sq) {
+            if (n < ORCA_MAX_OBST_NEIGHBORS) {
+              int i = n++;
+              while (i != 0 && d < od[i - 1]) {
+                od[i] = od[i - 1];
+                oid[i] = oid[i - 1];
+                --i;
+              }
+              od[i] = d;
+              oid[i] = v1;
+            } else {
+              *overflow = true;
+              // keep the nearest ORCA_MAX_OBST_NEIGHBORS: insert only if closer than the last
+              if (d < od[n - 1]) {
+                int i = n - 1;
+                while (i != 0 && d < od[i - 1]) {
+                  od[i] = od[i - 1];
+                  oid[i] = oid[i - 1];
+                  --i;
+                }
+                od[i] = d;
+                oid[i] = v1;
+              }
+            }
+          }
+        }
+        if (far_c >= 0 && sp < ORCA_MAX_BSP_DEPTH) stk[sp++] = far_c << 1;
+      }
+    }
+  }
+  *cnt = n;
+}
+
+// ---- obstacle half-planes (first half) ------------------------------------------------------
+// Appends at most ORCA_MAX_OBST_LINES lines to L starting at index 0; returns their number.
+template <class LS>
+ORCA_HD int obstacle_lines(const ObstacleWorld& W, float2 p, float2 vel, float radius, float inv_tho,
+                           const float* od, const int* oid, int cnt, const LS& L, bool* overflow) {
+  (void)od;
+  int nl = 0;
+  const float r_sq = sqr(radius);
+  for (int q = 0; q < cnt; ++q) {
+    int o1 = oid[q];
+    float4 a = ORCA_LDG(&W.vert_pd[o1]);
+    int4 la = ORCA_LDG(&W.vert_link[o1]);
+    int o2 = la.x;
+    float4 b = ORCA_LDG(&W.vert_pd[o2]);
+    int4 lb = ORCA_LDG(&W.vert_link[o2]);
+    float2 p1 = v2(a.x, a.y), p2 = v2(b.x, b.y);
+    float2 dir1 = v2(a.z, a.w), dir2 = v2(b.z, b.w);
+    bool cvx1 = la.z != 0, cvx2 = lb.z != 0;
+    const float2 rp1 = sub(p1, p), rp2 = sub(p2, p);
+
+    bool covered = false;
+    for (int j = 0; j < nl; ++j) {
+      const float4 lj = L.get(j);
+      if (det(sub(mul(inv_tho, rp1), pt(lj)), dr(lj)) - inv_tho * radius >= -kEps &&
+          det(sub(mul(inv_tho, rp2), pt(lj)), dr(lj)) - inv_tho * radius >= -kEps) {
+        covered = true;
+        break;
+      }
+    }
+    if (covered) continue;
+
+    const float d1 = abs_sq(rp1), d2 = abs_sq(rp2);
+    const float2 ov = sub(p2, p1);
+    const float s = dot(neg(rp1), ov) / abs_sq(ov);
+    const float d_line = abs_sq(sub(neg(rp1), mul(s, ov)));
+
+    float2 out_pt = v2(0.f, 0.f), out_dir = v2(0.f, 0.f);
+    bool emit = false;
+    bool finished = false;
+
+    if (s < 0.f && d1 <= r_sq) {
+      if (cvx1) {
+        out_dir = unit(v2(-rp1.y, rp1.x));
+        emit = true;
+      }
+      finished = true;
+    } else if (s > 1.f && d2 <= r_sq) {
+      if (cvx2 && det(rp2, dir2) >= 0.f) {
+        out_dir = unit(v2(-rp2.y, rp2.x));
+        emit = true;
+      }
+      finished = true;
+    } else if (s >= 0.f && s < 1.f && d_line <= r_sq) {
+      out_dir = neg(dir1);
+      emit = true;
+      finished = true;
+    }
+
+    if (!finished) {
+      float2 left_leg, right_leg;
+      bool same = false;  // obstacle1 == obstacle2
+      bool skip = false;
+      if (s < 0.f && d_line <= r_sq) {
+        if (!cvx1) {
+          skip = true;
+        } else {
+          // viewed obliquely: both legs come from the left vertex
+          o2 = o1;
+          p2 = p1;
+          dir2 = dir1;
+          cvx2 = cvx1;
+          same = true;
+          const float leg1 = sqrtf(d1 - r_sq);
+          left_leg = div_s(v2(rp1.x * leg1 - rp1.y * radius, rp1.x * radius + rp1.y * leg1), d1);
+          right_leg = div_s(v2(rp1.x * leg1 + rp1.y * radius, -rp1.x * radius + rp1.y * leg1), d1);
+        }
+      } else if (s > 1.f && d_line <= r_sq) {
+        if (!cvx2) {
+          skip = true;
+        } else {
+          o1 = o2;
+          p1 = p2;
+          dir1 = dir2;
+          cvx1 = cvx2;
+          la = lb;
+          same = true;
+          const float leg2 = sqrtf(d2 - r_sq);
+          left_leg = div_s(v2(rp2.x * leg2 - rp2.y * radius, rp2.x * radius + rp2.y * leg2), d2);
+          right_leg = div_s(v2(rp2.x * leg2 + rp2.y * radius, -rp2.x * radius + rp2.y * leg2), d2);
+        }
+      } else {
+        if (cvx1) {
+          const float leg1 = sqrtf(d1 - r_sq);
+          left_leg = div_s(v2(rp1.x * leg1 - rp1.y * radius, rp1.x * radius + rp1.y * leg1), d1);
+        } else {
+          left_leg = neg(dir1);
+        }
+        if (cvx2) {
+          const float leg2 = sqrtf(d2 - r_sq);
+          right_leg = div_s(v2(rp2.x * leg2 + rp2.y * radius, -rp2.x * radius + rp2.y * leg2), d2);
+        } else {
+          right_leg = dir1;
+        }
+      }
+      if (!skip) {
+        // a leg may not point into the neighboring edge of a convex vertex: use that edge's
+        // cut-off line instead and remember that the leg is "foreign"
+        const int left_nbr = la.y;  // obstacle1->prev
+        const float4 ln = ORCA_LDG(&W.vert_pd[left_nbr]);
+        const float2 ln_dir = v2(ln.z, ln.w);
+        bool left_foreign = false, right_foreign = false;
+        if (cvx1 && det(left_leg, neg(ln_dir)) >= 0.f) {
+          left_leg = neg(ln_dir);
+          left_foreign = true;
+        }
+        if (cvx2 && det(right_leg, dir2) <= 0.f) {
+          right_leg = dir2;
+          right_foreign = true;
+        }
+        const float2 lc = mul(inv_tho, sub(p1, p));
+        const float2 rc = mul(inv_tho, sub(p2, p));
+        const float2 cv = sub(rc, lc);
+        const float t = same ? 0.5f : dot(sub(vel, lc), cv) / abs_sq(cv);
+        const float t_left = dot(sub(vel, lc), left_leg);
+        const float t_right = dot(sub(vel, rc), right_leg);
+        if ((t < 0.f && t_left < 0.f) || (same && t_left < 0.f && t_right < 0.f)) {
+          const float2 uw = unit(sub(vel, lc));
+          out_dir = v2(uw.y, -uw.x);
+          out_pt = add(lc, mul(radius * inv_tho, uw));
+          emit = true;
+        } else if (t > 1.f && t_right < 0.f) {
+          const float2 uw = unit(sub(vel, rc));
+          out_dir = v2(uw.y, -uw.x);
+          out_pt = add(rc, mul(radius * inv_tho, uw));
+          emit = true;
+        } else {
+          const float inf = INFINITY;
+          const float dc = (t < 0.f || t > 1.f || same) ? inf : abs_sq(sub(vel, add(lc, mul(t, cv))));
+          const float dl = (t_left < 0.f) ? inf : abs_sq(sub(vel, add(lc, mul(t_left, left_leg))));
+          const float drr = (t_right < 0.f) ? inf : abs_sq(sub(vel, add(rc, mul(t_right, right_leg))));
+          if (dc <= dl && dc <= drr) {
+            out_dir = neg(dir1);
+            out_pt = add(lc, mul(radius * inv_tho, v2(-out_dir.y, out_dir.x)));
+            emit = true;
+          } else if (dl <= drr) {
+            if (!left_foreign) {
+              out_dir = left_leg;
+              out_pt = add(lc, mul(radius * inv_tho, v2(-out_dir.y, out_dir.x)));
+              emit = true;
+            }
+          } else {
+            if (!right_foreign) {
+              out_dir = neg(right_leg);
+              out_pt = add(rc, mul(radius * inv_tho, v2(-out_dir.y, out_dir.x)));
+              emit = true;
+            }
+          }
+        }
+      }
+    }
+    if (emit) {
+      if (nl < ORCA_MAX_OBST_LINES) {
+        L.set(nl++, out_pt, out_dir);
+      } else {
+        *overflow = true;
+      }
+    }
+  }
+  return nl;
+}
+
+// ---- goal-directed preferred velocity ----------------------------------------------------------------
+// (cos, sin) of atan2(goal - pos)  ==  unit(goal - pos); atan2(0, 0) = 0 gives (1, 0)
+// (collision_avoidence_env.py:156-162, ALAN_true.py:489-495).
+ORCA_HD float2 goal_direction(float2 pos, float2 goal) {
+  const float2 d = sub(goal, pos);
+  const float n2 = abs_sq(d);
+  if (n2 > 0.f) {
+    const float inv = 1.0f / sqrtf(n2);
+    return v2(d.x * inv, d.y * inv);
+  }
+  return v2(1.f, 0.f);
+}
+// rotate unit vector `a` by the angle of unit vector `b`: (cos(ta+tb), sin(ta+tb))
+ORCA_HD float2 rotate(float2 a, float2 b) { return v2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// ---- Philox4x32-10 counter RNG (Salmon et al. 2011), one draw per (agent, step) ---------------------
+ORCA_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+ORCA_HD float philox_uniform(uint64_t seed, uint32_t c0, uint32_t c1) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+    const uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
+    x0 = y0;
+    x1 = y1;
+    x2 = y2;
+    x3 = y3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  // 24 high bits -> [0, 1)
+  return (float)(x0 >> 8) * (1.0f / 16777216.0f);
+}
+
+}  // namespace orca

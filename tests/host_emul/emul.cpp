@@ -1,0 +1,82 @@
+// emul.cpp -- TEST-ONLY host emulation of the fused step kernel.
+//
+// Compiles the library's own per-agent device code (csrc/orca_core.cuh, agent_step_body in
+// csrc/orca_step_small.cuh) with g++ and runs it serially over a batch.  It lets the CPU test
+// suite check the kernel LOGIC against the oracle without a GPU.  It is not a fallback: the
+// package never loads it, and the GPU parity tests run the real CUDA path.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+static inline void sincosf_(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+#define sincosf sincosf_
+#include "../../collision_avoidance_b200/csrc/obstacle_world.h"
+#include "../../collision_avoidance_b200/csrc/orca_step_small.cuh"
+
+namespace {
+template <int K>
+void run_k(const orca::StepArgs& a, int policy) {
+  const int E = a.E, N = a.N;
+  std::vector<float2> spos((size_t)N), svel((size_t)N);
+  std::vector<float4> lines((size_t)(K + ORCA_MAX_OBST_LINES));
+  for (int e = 0; e < E; ++e) {
+    for (int i = 0; i < N; ++i) {
+      spos[(size_t)i] = a.pos[(size_t)e * N + i];
+      svel[(size_t)i] = a.vel[(size_t)e * N + i];
+    }
+    const int estep = a.env_step ? a.env_step[e] : 0;
+    for (int i = 0; i < N; ++i) {
+      orca::Lines L;
+      L.base = lines.data();
+      L.stride = 1;
+      const int g = e * N + i;
+      switch (policy) {
+        case 0: orca::agent_step_body<K, 0>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L); break;
+        case 1: orca::agent_step_body<K, 1>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L); break;
+        case 2: orca::agent_step_body<K, 2>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L); break;
+        default: orca::agent_step_body<K, 3>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L); break;
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// Mirrors orca_set_obstacles + the table packing of orca_api.cu for ONE shared world.
+// Returns number of vertices; fills pd[v*4], link[v*4], bsp[v*4] (caller allocates max_v rows).
+int emul_build_world(const float* xy, const int* poly_sizes, int num_polys, int max_v, float* pd, int* link, int* bsp,
+                     int* depth) {
+  orca_host::ObstacleTables T;
+  size_t off = 0;
+  for (int p = 0; p < num_polys; ++p) {
+    if (orca_host::add_polygon(T, xy + 2 * off, poly_sizes[p]) < 0) return -1;
+    off += (size_t)poly_sizes[p];
+  }
+  orca_host::process(T);
+  const int nv = T.num_vertices();
+  if (nv > max_v) return -2;
+  for (int v = 0; v < nv; ++v) {
+    pd[4 * v] = T.px[v]; pd[4 * v + 1] = T.py[v]; pd[4 * v + 2] = T.ux[v]; pd[4 * v + 3] = T.uy[v];
+    link[4 * v] = T.next[v]; link[4 * v + 1] = T.prev[v]; link[4 * v + 2] = T.convex[v]; link[4 * v + 3] = 0;
+    bsp[4 * v] = T.node_vertex[v]; bsp[4 * v + 1] = T.node_left[v]; bsp[4 * v + 2] = T.node_right[v]; bsp[4 * v + 3] = 0;
+  }
+  *depth = T.depth;
+  return nv;
+}
+
+// args: a fully populated orca::StepArgs with HOST pointers.
+int emul_step(const orca::StepArgs* a, int policy) {
+  if (a->k <= 5) run_k<5>(*a, policy);
+  else if (a->k <= 10) run_k<10>(*a, policy);
+  else if (a->k <= 16) run_k<16>(*a, policy);
+  else return -1;
+  return 0;
+}
+
+int emul_stepargs_size() { return (int)sizeof(orca::StepArgs); }
+
+float emul_philox_uniform(unsigned long long seed, unsigned c0, unsigned c1) { return orca::philox_uniform(seed, c0, c1); }
+
+}  // extern "C"
