@@ -50,6 +50,7 @@ struct OrcaSim {
   float4* d_vert_pd = nullptr;
   int4* d_vert_link = nullptr;
   int4* d_bsp = nullptr;
+  float4* d_bsp_seg = nullptr;
   int* d_env_nodes = nullptr;
   int shared_nodes = 0;
   int vert_stride = 0;
@@ -69,10 +70,12 @@ void free_obstacles(OrcaSim* s) {
   cudaFree(s->d_vert_pd);
   cudaFree(s->d_vert_link);
   cudaFree(s->d_bsp);
+  cudaFree(s->d_bsp_seg);
   cudaFree(s->d_env_nodes);
   s->d_vert_pd = nullptr;
   s->d_vert_link = nullptr;
   s->d_bsp = nullptr;
+  s->d_bsp_seg = nullptr;
   s->d_env_nodes = nullptr;
   s->shared_nodes = 0;
   s->vert_stride = 0;
@@ -103,12 +106,13 @@ void fill_common(const OrcaSim* s, orca::StepArgs* a) {
   a->vert_pd = s->d_vert_pd;
   a->vert_link = s->d_vert_link;
   a->bsp = s->d_bsp;
+  a->bsp_seg = s->d_bsp_seg;
   a->env_nodes = s->per_env ? s->d_env_nodes : nullptr;
   a->shared_nodes = s->shared_nodes;
   a->vert_stride = s->per_env ? s->vert_stride : 0;
 }
 
-template <int K, int POLICY>
+template <int K, bool KFULL, int POLICY>
 int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   const int N = s->N;
   const int tpb = (N <= 128) ? 128 : 256;
@@ -116,7 +120,7 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   args.envs_per_block = tpb / N;
   const int blocks = (s->E + args.envs_per_block - 1) / args.envs_per_block;
   const size_t smem = (size_t)tpb * (16 + (size_t)(K + ORCA_MAX_OBST_LINES) * 16);
-  auto kern = orca::step_small_kernel<K, POLICY>;
+  auto kern = orca::step_small_kernel<K, KFULL, POLICY>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * (16 + (K + ORCA_MAX_OBST_LINES) * 16)));
@@ -128,17 +132,17 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   return ORCA_OK;
 }
 
-template <int K>
+template <int K, bool KFULL>
 int launch_small_k(OrcaSim* s, const orca::StepArgs& a, int policy, cudaStream_t st) {
   switch (policy) {
     case ORCA_POLICY_EXTERNAL:
-      return launch_small_kp<K, orca::POLICY_EXTERNAL>(s, a, st);
+      return launch_small_kp<K, KFULL, orca::POLICY_EXTERNAL>(s, a, st);
     case ORCA_POLICY_GOAL:
-      return launch_small_kp<K, orca::POLICY_GOAL>(s, a, st);
+      return launch_small_kp<K, KFULL, orca::POLICY_GOAL>(s, a, st);
     case ORCA_POLICY_RL:
-      return launch_small_kp<K, orca::POLICY_RL>(s, a, st);
+      return launch_small_kp<K, KFULL, orca::POLICY_RL>(s, a, st);
     case ORCA_POLICY_ALAN:
-      return launch_small_kp<K, orca::POLICY_ALAN>(s, a, st);
+      return launch_small_kp<K, KFULL, orca::POLICY_ALAN>(s, a, st);
     default:
       return fail(ORCA_ERR_INVALID, "unknown policy %d", policy);
   }
@@ -148,16 +152,11 @@ int launch_step(OrcaSim* s, const orca::StepArgs& a, int policy, cudaStream_t st
   if (s->N > 256) {
     return orca::launch_grid_step(s->grid, a, policy, st, &s->launches, &g_last_error);
   }
-  switch (pick_k(s->p.max_neighbors)) {
-    case 5:
-      return launch_small_k<5>(s, a, policy, st);
-    case 10:
-      return launch_small_k<10>(s, a, policy, st);
-    case 16:
-      return launch_small_k<16>(s, a, policy, st);
-    default:
-      return fail(ORCA_ERR_UNSUPPORTED, "max_neighbors=%d > 16 is not supported", s->p.max_neighbors);
-  }
+  const int k = s->p.max_neighbors;
+  if (k == 5) return launch_small_k<5, true>(s, a, policy, st);
+  if (k == 10) return launch_small_k<10, true>(s, a, policy, st);
+  if (k <= 16) return launch_small_k<16, false>(s, a, policy, st);
+  return fail(ORCA_ERR_UNSUPPORTED, "max_neighbors=%d > 16 is not supported", k);
 }
 
 int ensure_host_staging(OrcaSim* s) {
@@ -253,7 +252,7 @@ int orca_set_obstacles(OrcaSim* s, const float* xy, const int32_t* poly_sizes, i
   int stride = 0;
   for (const auto& T : s->worlds) stride = T.num_vertices() > stride ? T.num_vertices() : stride;
   if (stride == 0) return ORCA_OK;  // no obstacles at all
-  std::vector<float4> pd((size_t)n_worlds * stride);
+  std::vector<float4> pd((size_t)n_worlds * stride), seg((size_t)n_worlds * stride);
   std::vector<int4> link((size_t)n_worlds * stride), bsp((size_t)n_worlds * stride);
   std::vector<int> nodes((size_t)n_worlds);
   for (int w = 0; w < n_worlds; ++w) {
@@ -268,15 +267,21 @@ int orca_set_obstacles(OrcaSim* s, const float* xy, const int32_t* poly_sizes, i
         pd[o] = make_float4(0, 0, 1, 0);
         link[o] = make_int4(0, 0, 0, 0);
       }
-      if (v < T.num_nodes())
-        bsp[o] = make_int4(T.node_vertex[v], T.node_left[v], T.node_right[v], 0);
-      else
+      if (v < T.num_nodes()) {
+        const int e1 = T.node_vertex[v], e2 = T.next[e1];
+        bsp[o] = make_int4(e1, T.node_left[v], T.node_right[v], 0);
+        seg[o] = make_float4(T.px[e1], T.py[e1], T.px[e2], T.py[e2]);
+      } else {
         bsp[o] = make_int4(0, -1, -1, 0);
+        seg[o] = make_float4(0, 0, 1, 0);
+      }
     }
   }
   CUDA_TRY(cudaMalloc(&s->d_vert_pd, pd.size() * sizeof(float4)));
   CUDA_TRY(cudaMalloc(&s->d_vert_link, link.size() * sizeof(int4)));
   CUDA_TRY(cudaMalloc(&s->d_bsp, bsp.size() * sizeof(int4)));
+  CUDA_TRY(cudaMalloc(&s->d_bsp_seg, seg.size() * sizeof(float4)));
+  CUDA_TRY(cudaMemcpy(s->d_bsp_seg, seg.data(), seg.size() * sizeof(float4), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(s->d_vert_pd, pd.data(), pd.size() * sizeof(float4), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(s->d_vert_link, link.data(), link.size() * sizeof(int4), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(s->d_bsp, bsp.data(), bsp.size() * sizeof(int4), cudaMemcpyHostToDevice));

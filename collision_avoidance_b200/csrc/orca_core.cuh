@@ -38,6 +38,13 @@
 #endif
 #define ORCA_MAX_BSP_DEPTH 64
 
+#if defined(ORCA_EMUL_COUNT) && !defined(__CUDA_ARCH__)
+extern long long g_orca_counters[16];
+#define ORCA_COUNT(slot, n) (g_orca_counters[slot] += (n))
+#else
+#define ORCA_COUNT(slot, n) ((void)0)
+#endif
+
 namespace orca {
 
 constexpr float kEps = 0.00001f;  // RVO_EPSILON
@@ -98,10 +105,13 @@ ORCA_HD float2 dr(float4 l) { return v2(l.z, l.w); }
 // vert_pd[v]   = (point.x, point.y, unitDir.x, unitDir.y)
 // vert_link[v] = (next, prev, isConvex, 0)
 // bsp[n]       = (vertex, left child, right child, 0); node 0 is the root; -1 = no child
+// bsp_seg[n]   = (p1.x, p1.y, p2.x, p2.y) of the node's edge, so that a visit is two independent
+//                16-byte loads instead of a node -> vertex -> next-vertex pointer chase
 struct ObstacleWorld {
   const float4* vert_pd;
   const int4* vert_link;
   const int4* bsp;
+  const float4* bsp_seg;
   int n_nodes;
 };
 
@@ -123,6 +133,8 @@ ORCA_HD bool lp1(const LS& L, int i, float radius, float2 opt, bool dir_opt, flo
   const float sq = sqrtf(disc);
   float t_lo = -dp - sq;
   float t_hi = -dp + sq;
+  ORCA_COUNT(2, 1);  // lp1 calls
+  ORCA_COUNT(3, i);  // lp1 inner iterations (upper bound)
   for (int j = 0; j < i; ++j) {
     const float4 lj = L.get(j);
     const float den = det(di, dr(lj));
@@ -152,11 +164,25 @@ ORCA_HD bool lp1(const LS& L, int i, float radius, float2 opt, bool dir_opt, flo
   return true;
 }
 
+// Warp-synchronous control flow.  LP2/LP3 are data-dependent nested loops; left to the
+// compiler, lanes that fail LP2 at different lines jump straight into LP3 and never meet
+// again (measured: 2-5 of 32 lanes active in LP3).  Instead every loop below runs
+// "while ANY lane of the warp still has work", so all lanes of `mask` stay in lock step:
+// each round is [skip to my next violated line] -> converge -> [LP1 / projection] for the
+// lanes that have one.  `mask` = lanes of the warp that execute the step (all of them call
+// lp2/lp3, lanes without work pass enabled = false).  On the host the vote is the lane itself.
+#if defined(__CUDA_ARCH__)
+#define ORCA_ANY(mask, pred) __any_sync((mask), (pred))
+#define ORCA_CONVERGE(mask) __syncwarp(mask)
+#else
+#define ORCA_ANY(mask, pred) (pred)
+#define ORCA_CONVERGE(mask) ((void)0)
+#endif
+
 // LP2: returns the index of the first line that cannot be satisfied (n on success).
-// Written as "skip to the next violated line, then run LP1" so that diverged lanes of a
-// warp meet again at every LP1 instead of serialising one LP1 per line index.
 template <class LS>
-ORCA_HD int lp2(const LS& L, int n, float radius, float2 opt, bool dir_opt, float2& result) {
+ORCA_HD int lp2(unsigned mask, bool enabled, const LS& L, int n, float radius, float2 opt, bool dir_opt,
+                float2& result) {
   if (dir_opt) {
     result = mul(radius, opt);  // opt * radius
   } else if (abs_sq(opt) > sqr(radius)) {
@@ -165,32 +191,56 @@ ORCA_HD int lp2(const LS& L, int n, float radius, float2 opt, bool dir_opt, floa
     result = opt;
   }
   int i = 0;
-  for (;;) {
-    while (i < n) {
-      const float4 li = L.get(i);
-      if (det(dr(li), sub(pt(li), result)) > 0.f) break;
+  int fail = n;
+  bool active = enabled;
+  while (ORCA_ANY(mask, active)) {
+    if (active) {
+      while (i < n) {
+        const float4 li = L.get(i);
+        if (det(dr(li), sub(pt(li), result)) > 0.f) break;
+        ++i;
+      }
+      active = i < n;
+    }
+    ORCA_CONVERGE(mask);
+    if (active) {
+      const float2 keep = result;
+      if (!lp1(L, i, radius, opt, dir_opt, result)) {
+        result = keep;
+        fail = i;
+        active = false;
+      }
       ++i;
     }
-    if (i >= n) return n;
-    const float2 keep = result;
-    if (!lp1(L, i, radius, opt, dir_opt, result)) {
-      result = keep;
-      return i;
-    }
-    ++i;
   }
+  return fail;
 }
 
 // LP3: minimise the maximum violation of the agent lines [n_obst, n), obstacle lines hard.
-// `P` is scratch line storage for the projected programme (at least n entries).
+// `P` is scratch line storage for the projected programme (at least n entries).  Lanes with
+// need = false only take part in the votes.
 template <class LS, class PS>
-ORCA_HD void lp3(const LS& L, int n, int n_obst, int begin, float radius, const PS& P, float2& result) {
+ORCA_HD void lp3(unsigned mask, bool need, const LS& L, int n, int n_obst, int begin, float radius, const PS& P,
+                 float2& result) {
   float distance = 0.f;
-  for (int i = begin; i < n; ++i) {
-    const float4 li = L.get(i);
-    const float2 pi = pt(li), di = dr(li);
-    if (det(di, sub(pi, result)) > distance) {
-      int m = 0;
+  int i = begin;
+  bool active = need;
+  while (ORCA_ANY(mask, active)) {
+    float2 pi = v2(0.f, 0.f), di = v2(0.f, 0.f);
+    if (active) {
+      while (i < n) {
+        const float4 li = L.get(i);
+        pi = pt(li);
+        di = dr(li);
+        if (det(di, sub(pi, result)) > distance) break;
+        ++i;
+      }
+      active = i < n;
+    }
+    ORCA_CONVERGE(mask);
+    int m = 0;
+    if (active) {
+      ORCA_COUNT(0, 1);  // lp3 rounds
       for (int j = 0; j < n_obst; ++j) {
         const float4 lj = L.get(j);
         P.set(m++, pt(lj), dr(lj));
@@ -207,10 +257,16 @@ ORCA_HD void lp3(const LS& L, int n, int n_obst, int begin, float radius, const 
           np = add(pi, mul(det(dj, sub(pi, pj)) / d, di));
         }
         P.set(m++, np, unit(sub(dj, di)));
+        ORCA_COUNT(1, 1);  // projected lines
       }
-      const float2 keep = result;
-      if (lp2(P, m, radius, v2(-di.y, di.x), true, result) < m) result = keep;
+    }
+    ORCA_CONVERGE(mask);
+    float2 cand = result;
+    const int f = lp2(mask, active, P, m, radius, v2(-di.y, di.x), true, cand);
+    if (active) {
+      if (!(f < m)) result = cand;  // on failure keep the previous result
       distance = det(di, sub(pi, result));
+      ++i;
     }
   }
 }
@@ -263,21 +319,30 @@ ORCA_HD float4 agent_line(float2 p, float2 v, float2 po, float2 vo, float cr, fl
 // start at rangeSq, which makes the strict `<` test do double duty as RVO2's range test and its
 // "shrink the range to the k-th best" rule.  Equal distances keep the earlier
 // entry in front (first visited wins); callers visit candidates in ascending agent id.
-template <int K>
+// KFULL = the runtime k equals K, so the acceptance threshold is simply the last slot; every
+// index below is a compile-time constant, which keeps both arrays in registers.
+template <int K, bool KFULL>
 struct NearestK {
   float d[K];
   int id[K];
-  float thresh;
   ORCA_HD void init(int k, float range_sq) {
 #pragma unroll
     for (int s = 0; s < K; ++s) {
-      d[s] = (s < k) ? range_sq : -1.0f;
+      d[s] = (KFULL || s < k) ? range_sq : -1.0f;
       id[s] = -1;
     }
-    thresh = (k > 0) ? range_sq : -1.0f;
   }
-  ORCA_HD void offer(float cand_d, int cand_id, int k) {
-    if (cand_d < thresh) {
+  // current acceptance threshold: distance of the k-th slot (slots >= k are -1, distances >= 0,
+  // and the list is ascending, so that is the maximum over all slots)
+  ORCA_HD float thresh() const {
+    if (KFULL) return d[K - 1];
+    float m = d[0];
+#pragma unroll
+    for (int s = 1; s < K; ++s) m = fmaxf(m, d[s]);
+    return m;
+  }
+  ORCA_HD void offer(float cand_d, int cand_id) {
+    if (cand_d < thresh()) {
       float cd = cand_d;
       int ci = cand_id;
 #pragma unroll
@@ -289,15 +354,8 @@ struct NearestK {
         id[s] = sw ? ci : ti;
         cd = sw ? td : cd;
         ci = sw ? ti : ci;
-        if (s == k - 1) thresh = d[s];
       }
     }
-  }
-  ORCA_HD int count() const {
-    int c = 0;
-#pragma unroll
-    for (int s = 0; s < K; ++s) c += (id[s] >= 0) ? 1 : 0;
-    return c;
   }
 };
 
@@ -317,11 +375,9 @@ ORCA_HD void obstacle_neighbors(const ObstacleWorld& W, float2 p, float range_sq
       const int top = stk[sp - 1];
       const int node = top >> 1;
       const int4 nd = ORCA_LDG(&W.bsp[node]);
+      const float4 sg = ORCA_LDG(&W.bsp_seg[node]);
       const int v1 = nd.x;
-      const float4 a = ORCA_LDG(&W.vert_pd[v1]);
-      const int v2i = ORCA_LDG(&W.vert_link[v1]).x;
-      const float4 b = ORCA_LDG(&W.vert_pd[v2i]);
-      const float2 p1 = v2(a.x, a.y), p2 = v2(b.x, b.y);
+      const float2 p1 = v2(sg.x, sg.y), p2 = v2(sg.z, sg.w);
       const float side = left_of(p1, p2, p);
       const int near_c = (side >= 0.f) ? nd.y : nd.z;
       const int far_c = (side >= 0.f) ? nd.z : nd.y;

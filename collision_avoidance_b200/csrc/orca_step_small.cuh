@@ -74,6 +74,7 @@ struct StepArgs {
   const float4* vert_pd;
   const int4* vert_link;
   const int4* bsp;
+  const float4* bsp_seg;
   const int* env_nodes;  // per-env node count, or NULL when the world is shared
   int shared_nodes;      // node count of the shared world
   int vert_stride;       // per-env table stride (0 when shared)
@@ -124,9 +125,10 @@ ORCA_HD void counter_inc(int* c) {
 // Everything one agent does in one fused step.  `env_pos` / `env_vel` are the PRE-step
 // snapshot of the agent's env (shared memory in the kernel), `L` its private line storage,
 // (p, v) its own pre-step state, `estep` the env's step counter before this step.
-template <int K, int POLICY>
+template <int K, bool KFULL, int POLICY>
 ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, const int g, float2 p, float2 v,
-                             const int estep, const float2* env_pos, const float2* env_vel, const Lines L) {
+                             const int estep, const float2* env_pos, const float2* env_vel, const Lines L,
+                             const unsigned warp_mask) {
   const int N = a.N;
 
   // ---------------- preferred velocity (policy) ----------------
@@ -184,6 +186,7 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
     W.vert_pd = a.vert_pd + voff;
     W.vert_link = a.vert_link + voff;
     W.bsp = a.bsp + voff;
+    W.bsp_seg = a.bsp_seg + voff;
     W.n_nodes = (a.env_nodes != nullptr) ? a.env_nodes[env] : a.shared_nodes;
   }
   bool overflow = false;
@@ -192,13 +195,13 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
   int ocnt = 0;
   if (W.n_nodes > 0) obstacle_neighbors(W, p, a.obst_range_sq, od, oid, &ocnt, &overflow);
 
-  NearestK<K> nk;
+  NearestK<K, KFULL> nk;
   nk.init(a.k, a.nd_sq);
   {
     for (int j = 0; j < N; ++j) {
       if (j == la) continue;
       const float2 q = env_pos[j];
-      nk.offer(abs_sq(sub(p, q)), j, a.k);
+      nk.offer(abs_sq(sub(p, q)), j);
     }
   }
 
@@ -242,13 +245,14 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
 
   // ---------------- linear programs ----------------
   float2 nv;
-  const int fail = lp2(L, n, a.vmax, pref, false, nv);
-  if (fail < n) {
+  const int fail = lp2(warp_mask, true, L, n, a.vmax, pref, false, nv);
+  {
+    // every lane takes part (warp-synchronous loops); only lanes whose LP2 failed do work
     float4 proj[K + ORCA_MAX_OBST_LINES];
     LocalLines P;
     P.base = proj;
-    lp3(L, n, n_obst, fail, a.vmax, P, nv);
-    stat_add_u64(a.stats, STAT_LP3_CALLS, 1ull);
+    lp3(warp_mask, fail < n, L, n, n_obst, fail, a.vmax, P, nv);
+    if (fail < n) stat_add_u64(a.stats, STAT_LP3_CALLS, 1ull);
   }
 
   // ---------------- integrate (Agent::update) ----------------
@@ -307,8 +311,16 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
 
 #if defined(__CUDACC__)
 
-template <int K, int POLICY>
-__global__ void __launch_bounds__(256, 2) step_small_kernel(const StepArgs a) {
+// register budget of the step kernel: 65536 / (threads * min blocks) registers per thread
+#ifndef ORCA_STEP_MAX_THREADS
+#define ORCA_STEP_MAX_THREADS 256
+#endif
+#ifndef ORCA_STEP_MIN_BLOCKS
+#define ORCA_STEP_MIN_BLOCKS 3
+#endif
+
+template <int K, bool KFULL, int POLICY>
+__global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) step_small_kernel(const StepArgs a) {
   extern __shared__ float4 smem4[];
   const int tpb = blockDim.x;
   float2* s_pos = reinterpret_cast<float2*>(smem4);
@@ -333,11 +345,12 @@ __global__ void __launch_bounds__(256, 2) step_small_kernel(const StepArgs a) {
     if (a.env_step != nullptr) estep = a.env_step[env];
   }
   __syncthreads();
+  const unsigned warp_mask = __ballot_sync(0xffffffffu, valid);  // lanes that run the step
   if (!valid) return;
   Lines L;
   L.base = s_lines + tid;
   L.stride = tpb;
-  agent_step_body<K, POLICY>(a, env, la, g, p, v, estep, s_pos + le * N, s_vel + le * N, L);
+  agent_step_body<K, KFULL, POLICY>(a, env, la, g, p, v, estep, s_pos + le * N, s_vel + le * N, L, warp_mask);
 }
 
 #endif  // __CUDACC__

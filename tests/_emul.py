@@ -31,7 +31,7 @@ class StepArgs(ctypes.Structure):
         ("done_mode", c_i),
         ("nbr_idx", c_p), ("nbr_dsq", c_p), ("nbr_cnt", c_p), ("onbr_idx", c_p), ("onbr_cnt", c_p),
         ("stats", c_p),
-        ("vert_pd", c_p), ("vert_link", c_p), ("bsp", c_p), ("env_nodes", c_p),
+        ("vert_pd", c_p), ("vert_link", c_p), ("bsp", c_p), ("bsp_seg", c_p), ("env_nodes", c_p),
         ("shared_nodes", c_i), ("vert_stride", c_i), ("neighbors_only", c_i),
     ]
 
@@ -74,10 +74,11 @@ class World:
         self.pd = np.zeros((max_v, 4), np.float32)
         self.link = np.zeros((max_v, 4), np.int32)
         self.bsp = np.zeros((max_v, 4), np.int32)
+        self.seg = np.zeros((max_v, 4), np.float32)
         depth = c_i(0)
         nv = L.emul_build_world(c_p(xy.ctypes.data), c_p(sizes.ctypes.data), len(polygons), max_v,
                                 c_p(self.pd.ctypes.data), c_p(self.link.ctypes.data), c_p(self.bsp.ctypes.data),
-                                ctypes.byref(depth))
+                                c_p(self.seg.ctypes.data), ctypes.byref(depth))
         assert nv >= 0, nv
         self.nv = nv
         self.depth = depth.value
@@ -132,7 +133,7 @@ def emul_step(params, pos, vel, *, policy=0, pref=None, goal=None, goal2=None, w
         a.onbr_idx, a.onbr_cnt = _ptr(out["onbr_idx"]), _ptr(out["onbr_cnt"])
     a.stats = _ptr(stats)
     if world is not None and world.nv > 0:
-        a.vert_pd, a.vert_link, a.bsp = _ptr(world.pd), _ptr(world.link), _ptr(world.bsp)
+        a.vert_pd, a.vert_link, a.bsp, a.bsp_seg = _ptr(world.pd), _ptr(world.link), _ptr(world.bsp), _ptr(world.seg)
         a.shared_nodes, a.vert_stride = world.nv, 0
     a.neighbors_only = 1 if neighbors_only else 0
     rc = lib().emul_step(ctypes.byref(a), policy)

@@ -15,7 +15,7 @@ static inline void sincosf_(float x, float* s, float* c) { *s = sinf(x); *c = co
 #include "../../collision_avoidance_b200/csrc/orca_step_small.cuh"
 
 namespace {
-template <int K>
+template <int K, bool KFULL>
 void run_k(const orca::StepArgs& a, int policy) {
   const int E = a.E, N = a.N;
   std::vector<float2> spos((size_t)N), svel((size_t)N);
@@ -32,10 +32,10 @@ void run_k(const orca::StepArgs& a, int policy) {
       L.stride = 1;
       const int g = e * N + i;
       switch (policy) {
-        case 0: orca::agent_step_body<K, 0>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L); break;
-        case 1: orca::agent_step_body<K, 1>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L); break;
-        case 2: orca::agent_step_body<K, 2>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L); break;
-        default: orca::agent_step_body<K, 3>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L); break;
+        case 0: orca::agent_step_body<K, KFULL, 0>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L, 0xffffffffu); break;
+        case 1: orca::agent_step_body<K, KFULL, 1>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L, 0xffffffffu); break;
+        case 2: orca::agent_step_body<K, KFULL, 2>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L, 0xffffffffu); break;
+        default: orca::agent_step_body<K, KFULL, 3>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L, 0xffffffffu); break;
       }
     }
   }
@@ -47,7 +47,7 @@ extern "C" {
 // Mirrors orca_set_obstacles + the table packing of orca_api.cu for ONE shared world.
 // Returns number of vertices; fills pd[v*4], link[v*4], bsp[v*4] (caller allocates max_v rows).
 int emul_build_world(const float* xy, const int* poly_sizes, int num_polys, int max_v, float* pd, int* link, int* bsp,
-                     int* depth) {
+                     float* seg, int* depth) {
   orca_host::ObstacleTables T;
   size_t off = 0;
   for (int p = 0; p < num_polys; ++p) {
@@ -61,6 +61,8 @@ int emul_build_world(const float* xy, const int* poly_sizes, int num_polys, int 
     pd[4 * v] = T.px[v]; pd[4 * v + 1] = T.py[v]; pd[4 * v + 2] = T.ux[v]; pd[4 * v + 3] = T.uy[v];
     link[4 * v] = T.next[v]; link[4 * v + 1] = T.prev[v]; link[4 * v + 2] = T.convex[v]; link[4 * v + 3] = 0;
     bsp[4 * v] = T.node_vertex[v]; bsp[4 * v + 1] = T.node_left[v]; bsp[4 * v + 2] = T.node_right[v]; bsp[4 * v + 3] = 0;
+    const int e1 = T.node_vertex[v], e2 = T.next[e1];
+    seg[4 * v] = T.px[e1]; seg[4 * v + 1] = T.py[e1]; seg[4 * v + 2] = T.px[e2]; seg[4 * v + 3] = T.py[e2];
   }
   *depth = T.depth;
   return nv;
@@ -68,9 +70,9 @@ int emul_build_world(const float* xy, const int* poly_sizes, int num_polys, int 
 
 // args: a fully populated orca::StepArgs with HOST pointers.
 int emul_step(const orca::StepArgs* a, int policy) {
-  if (a->k <= 5) run_k<5>(*a, policy);
-  else if (a->k <= 10) run_k<10>(*a, policy);
-  else if (a->k <= 16) run_k<16>(*a, policy);
+  if (a->k == 5) run_k<5, true>(*a, policy);
+  else if (a->k == 10) run_k<10, true>(*a, policy);
+  else if (a->k <= 16) run_k<16, false>(*a, policy);
   else return -1;
   return 0;
 }
