@@ -6,6 +6,7 @@
 // -fmad=false is part of the contract: see orca_core.cuh.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -16,6 +17,7 @@
 #include "obstacle_world.h"
 #include "orca_core.cuh"
 #include "orca_grid.cuh"
+#include "orca_obs.cuh"
 #include "orca_step_small.cuh"
 
 namespace {
@@ -413,6 +415,53 @@ int orca_neighbors(OrcaSim* s, const float* pos_dev, int32_t* nbr_idx_dev, float
   a.onbr_cnt = obst_nbr_cnt_dev;
   a.neighbors_only = 1;
   return launch_step(s, a, ORCA_POLICY_EXTERNAL, static_cast<cudaStream_t>(stream));
+}
+
+int orca_observe(OrcaSim* s, const float* pos_dev, const float* vel_dev, const float* goal_dev, const int32_t* nbr_idx_dev,
+                 const int32_t* nbr_cnt_dev, const int32_t* obst_nbr_idx_dev, const int32_t* obst_nbr_cnt_dev, int laser_num,
+                 int circle_approx_num, float* obs_dev, void* stream) {
+  if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (!pos_dev || !vel_dev || !goal_dev || !nbr_idx_dev || !nbr_cnt_dev || !obst_nbr_idx_dev || !obst_nbr_cnt_dev || !obs_dev)
+    return fail(ORCA_ERR_INVALID, "orca_observe: null pointer argument");
+  if (laser_num < 1 || laser_num > ORCA_MAX_LASER) return fail(ORCA_ERR_UNSUPPORTED, "laser_num must be in [1, %d]", ORCA_MAX_LASER);
+  if (circle_approx_num < 3 || circle_approx_num > ORCA_MAX_CIRCLE_APPROX)
+    return fail(ORCA_ERR_UNSUPPORTED, "circle_approx_num must be in [3, %d]", ORCA_MAX_CIRCLE_APPROX);
+  CUDA_TRY(cudaSetDevice(s->device));
+  orca::ObsArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.E = s->E;
+  a.N = s->N;
+  a.k = s->p.max_neighbors > 0 ? s->p.max_neighbors : 1;
+  a.R = laser_num;
+  a.C = circle_approx_num;
+  a.pos = reinterpret_cast<const float2*>(pos_dev);
+  a.vel = reinterpret_cast<const float2*>(vel_dev);
+  a.goal = reinterpret_cast<const float2*>(goal_dev);
+  a.nbr_idx = nbr_idx_dev;
+  a.nbr_cnt = nbr_cnt_dev;
+  a.onbr_idx = obst_nbr_idx_dev;
+  a.onbr_cnt = obst_nbr_cnt_dev;
+  a.vert_pd = s->d_vert_pd;
+  a.vert_link = s->d_vert_link;
+  a.vert_stride = s->per_env ? s->vert_stride : 0;
+  a.obs = reinterpret_cast<float4*>(obs_dev);
+  // tables in float64 like the reference (env:321-350), rounded once to float32
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int i = 0; i < laser_num; ++i) {
+    const double th = i * (two_pi / laser_num);
+    a.ray_end[i] = make_float2((float)((double)s->p.neighbor_dist * std::cos(th)), (float)(-(double)s->p.neighbor_dist * std::sin(th)));
+  }
+  for (int i = 0; i < circle_approx_num; ++i) {
+    const double th = i * (two_pi / circle_approx_num);
+    a.poly[i] = make_float2((float)((double)s->p.radius * std::cos(th)), (float)(-(double)s->p.radius * std::sin(th)));
+  }
+  const long long total = (long long)s->E * s->N * laser_num;
+  const int tpb = 256;
+  const long long blocks = (total + tpb - 1) / tpb;
+  orca::observe_kernel<<<(unsigned)blocks, tpb, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  s->launches += 1;
+  return ORCA_OK;
 }
 
 int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pref_or_goal_host, int policy,

@@ -243,6 +243,24 @@ class BatchedRVOSimulator:
             a.stats_dev = self.stats.data_ptr()
         _lib.check(self._L.orca_env_step(self._h, ctypes.byref(a), self._stream()))
 
+    # ------------------------------------------------------------------ observation
+    def observe(self, goal: torch.Tensor, obs: Optional[torch.Tensor] = None, laser_num: int = 16,
+                circle_approx_num: int = 8) -> torch.Tensor:
+        """Laser-scan observation of every agent ([E, N, laser_num * 4] float32), from the current
+        positions / velocities and the neighbor lists of the last step that recorded them
+        (``env_step(want_neighbors=True)`` or ``neighbors()``) -- collision_avoidence_env.py:231-318."""
+        E, N = self.num_envs, self.agents_per_env
+        self._alloc_neighbor_outputs()
+        self._check_state(goal, (E, N, 2), torch.float32, "goal")
+        if obs is None:
+            obs = torch.empty(E, N, laser_num * 4, dtype=torch.float32, device=self.pos.device)
+        self._check_state(obs, (E, N, laser_num * 4), torch.float32, "obs")
+        _lib.check(self._L.orca_observe(self._h, self._p(self.pos), self._p(self.vel), self._p(goal),
+                                        self._p(self.nbr_idx), self._p(self.nbr_cnt), self._p(self.obst_nbr_idx),
+                                        self._p(self.obst_nbr_cnt), int(laser_num), int(circle_approx_num),
+                                        self._p(obs), self._stream()))
+        return obs
+
     # ------------------------------------------------------------------ host-buffer (e2e) path
     def step_host(self, pos_host: torch.Tensor, vel_host: torch.Tensor, pref_or_goal_host: torch.Tensor,
                   policy: int = _lib.POLICY_EXTERNAL, upload_state: bool = True, steps: int = 1):

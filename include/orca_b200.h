@@ -168,6 +168,15 @@ int orca_env_step(OrcaSim* sim, const OrcaEnvStepArgs* args, void* stream);
 int orca_neighbors(OrcaSim* sim, const float* pos_dev, int32_t* nbr_idx_dev, float* nbr_distsq_dev,
                    int32_t* nbr_cnt_dev, int32_t* obst_nbr_idx_dev, int32_t* obst_nbr_cnt_dev, void* stream);
 
+/* Laser-scan observation of every agent: Collision_Avoidance_Env._get_obs + utils.comp_laser
+ * (collision_avoidence_env.py:231-350 ; utils.py:5-113).  `laser_num` rays of length
+ * neighbor_dist per agent, neighbors approximated by `circle_approx_num`-gons of the agent
+ * radius; neighbor lists as written by orca_env_step / orca_neighbors.  obs_dev is
+ * [E*N][laser_num][4] = (hit.x, hit.y, vel.x, vel.y) in the goal-aligned frame. */
+int orca_observe(OrcaSim* sim, const float* pos_dev, const float* vel_dev, const float* goal_dev,
+                 const int32_t* nbr_idx_dev, const int32_t* nbr_cnt_dev, const int32_t* obst_nbr_idx_dev,
+                 const int32_t* obst_nbr_cnt_dev, int laser_num, int circle_approx_num, float* obs_dev, void* stream);
+
 /* Host-buffer variant of orca_step (the e2e path: what a PyRVOSimulator-style caller
  * pays): copies pref (and, if `upload_state`, pos/vel) host->device, steps `steps` times
  * with the given policy, copies pos/vel back, synchronises.  Buffers should be pinned. */

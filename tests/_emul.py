@@ -36,6 +36,16 @@ class StepArgs(ctypes.Structure):
     ]
 
 
+class ObsArgs(ctypes.Structure):
+    """Mirror of orca::ObsArgs (csrc/orca_obs.cuh)."""
+    _fields_ = [
+        ("E", c_i), ("N", c_i), ("k", c_i), ("R", c_i), ("C", c_i),
+        ("pos", c_p), ("vel", c_p), ("goal", c_p), ("nbr_idx", c_p), ("nbr_cnt", c_p), ("onbr_idx", c_p),
+        ("onbr_cnt", c_p), ("vert_pd", c_p), ("vert_link", c_p), ("vert_stride", c_i), ("obs", c_p),
+        ("ray_end", c_f * 64), ("poly", c_f * 32),
+    ]
+
+
 _lib = None
 
 
@@ -49,6 +59,8 @@ def lib():
         L = ctypes.CDLL(_LIB)
         L.emul_stepargs_size.restype = c_i
         assert L.emul_stepargs_size() == ctypes.sizeof(StepArgs), (L.emul_stepargs_size(), ctypes.sizeof(StepArgs))
+        assert L.emul_obsargs_size() == ctypes.sizeof(ObsArgs), (L.emul_obsargs_size(), ctypes.sizeof(ObsArgs))
+        L.emul_observe.argtypes = [ctypes.POINTER(ObsArgs), c_f, c_f]
         L.emul_step.argtypes = [ctypes.POINTER(StepArgs), c_i]
         L.emul_step.restype = c_i
         L.emul_build_world.restype = c_i
@@ -139,3 +151,19 @@ def emul_step(params, pos, vel, *, policy=0, pref=None, goal=None, goal2=None, w
     rc = lib().emul_step(ctypes.byref(a), policy)
     assert rc == 0
     return out
+
+
+def emul_observe(params, pos, vel, goal, nbr, world=None, laser_num=16, circle_approx_num=8):
+    """Laser scan of every agent (host emulation of observe_kernel).  nbr: dict from emul_step."""
+    E, N = pos.shape[0], pos.shape[1]
+    a = ObsArgs()
+    a.E, a.N, a.k, a.R, a.C = E, N, max(1, int(params["max_neighbors"])), laser_num, circle_approx_num
+    obs = np.zeros((E, N, laser_num * 4), np.float32)
+    a.pos, a.vel, a.goal = _ptr(pos), _ptr(vel), _ptr(goal)
+    a.nbr_idx, a.nbr_cnt, a.onbr_idx, a.onbr_cnt = (_ptr(nbr["nbr_idx"]), _ptr(nbr["nbr_cnt"]), _ptr(nbr["onbr_idx"]),
+                                                    _ptr(nbr["onbr_cnt"]))
+    if world is not None and world.nv > 0:
+        a.vert_pd, a.vert_link = _ptr(world.pd), _ptr(world.link)
+    a.obs = _ptr(obs)
+    assert lib().emul_observe(ctypes.byref(a), np.float32(params["neighbor_dist"]), np.float32(params["radius"])) == 0
+    return obs

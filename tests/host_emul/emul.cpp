@@ -13,6 +13,7 @@ static inline void sincosf_(float x, float* s, float* c) { *s = sinf(x); *c = co
 #define sincosf sincosf_
 #include "../../collision_avoidance_b200/csrc/obstacle_world.h"
 #include "../../collision_avoidance_b200/csrc/orca_step_small.cuh"
+#include "../../collision_avoidance_b200/csrc/orca_obs.cuh"
 
 namespace {
 template <int K, bool KFULL>
@@ -76,6 +77,25 @@ int emul_step(const orca::StepArgs* a, int policy) {
   else return -1;
   return 0;
 }
+
+// Laser observation for every (agent, ray); tables filled like orca_observe does.
+int emul_observe(orca::ObsArgs* a, float neighbor_dist, float radius) {
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int i = 0; i < a->R; ++i) {
+    const double th = i * (two_pi / a->R);
+    a->ray_end[i].x = (float)((double)neighbor_dist * std::cos(th));
+    a->ray_end[i].y = (float)(-(double)neighbor_dist * std::sin(th));
+  }
+  for (int i = 0; i < a->C; ++i) {
+    const double th = i * (two_pi / a->C);
+    a->poly[i].x = (float)((double)radius * std::cos(th));
+    a->poly[i].y = (float)(-(double)radius * std::sin(th));
+  }
+  for (int g = 0; g < a->E * a->N; ++g)
+    for (int r = 0; r < a->R; ++r) a->obs[(size_t)g * a->R + r] = orca::observe_ray(*a, g, r);
+  return 0;
+}
+int emul_obsargs_size() { return (int)sizeof(orca::ObsArgs); }
 
 int emul_stepargs_size() { return (int)sizeof(orca::StepArgs); }
 
