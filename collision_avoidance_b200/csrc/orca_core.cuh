@@ -341,6 +341,7 @@ struct NearestK {
     for (int s = 1; s < K; ++s) m = fmaxf(m, d[s]);
     return m;
   }
+  // Candidates arrive in ascending id: equal distances keep the earlier entry in front.
   ORCA_HD void offer(float cand_d, int cand_id) {
     if (cand_d < thresh()) {
       float cd = cand_d;
@@ -348,6 +349,27 @@ struct NearestK {
 #pragma unroll
       for (int s = 0; s < K; ++s) {
         const bool sw = cd < d[s];
+        const float td = d[s];
+        const int ti = id[s];
+        d[s] = sw ? cd : td;
+        id[s] = sw ? ci : ti;
+        cd = sw ? td : cd;
+        ci = sw ? ti : ci;
+      }
+    }
+  }
+  // Candidates arrive in arbitrary order (uniform-grid cells): order by (distance, rank) where
+  // `before(a, b)` says whether entry a precedes entry b at equal distance (b may be -1 = empty
+  // slot, which nothing precedes).  Gives the same list as ascending-id visiting.
+  template <class Before>
+  ORCA_HD void offer_ranked(float cand_d, int cand_id, const Before& before) {
+    if (cand_d <= thresh()) {
+      float cd = cand_d;
+      int ci = cand_id;
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        bool sw = cd < d[s];
+        if (cd == d[s]) sw = before(ci, id[s]);
         const float td = d[s];
         const int ti = id[s];
         d[s] = sw ? cd : td;

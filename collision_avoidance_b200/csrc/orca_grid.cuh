@@ -1,25 +1,452 @@
-// orca_grid.cuh -- uniform-grid neighbor pipeline for large worlds (agents_per_env > 256).
-// (first slice: interface only; the pipeline lands in a follow-up commit)
+// orca_grid.cuh -- uniform-grid neighbor pipeline for large worlds (agents_per_env > 256,
+// BASELINE config 5: one world of 1,000,000 agents).
+//
+// Replaces RVO2's per-step kd-tree (KdTree::buildAgentTree + queryAgentTreeRecursive, reached
+// through doStep: collision_avoidence_env.py:385,448 ; ALAN_true.py:601,632 ) by
+//   G1 grid_bounds    min/max of all positions                         (rd 8 B/agent)
+//   G2 grid_params    cell size = neighborDist, grid origin / dims     (1 thread)
+//   G3 grid_count     cell key per agent + slot inside the cell        (rd 8, wr 8, atomics)
+//   G4 grid_scan      exclusive scan of the cell populations           (3 small kernels)
+//   G5 grid_scatter   counting-sort scatter of pos / vel / id by cell  (rd 28, wr 20)
+//   G6 step_grid      fused step, candidates = the 3 x 3 cells around the agent
+// A counting sort by cell key is all the "cell-key sort" this needs: keys are dense small
+// integers, and the order inside a cell is irrelevant because equal distances are ranked by
+// agent id (NearestK::offer_ranked), which also makes the result independent of the atomics'
+// arrival order.  The sorted copies of pos / vel are the PRE-step snapshot every candidate read
+// goes to, so the step itself updates the caller's arrays in place (RVO2's two-phase doStep).
+//
+// Positions outside the grid box are clamped into the border cells: clamping is monotone and
+// 1-Lipschitz on cell coordinates, so two agents within one cell size of each other always
+// land in cells at most one apart -- the 3 x 3 scan never misses a neighbor.
 #pragma once
 
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#endif
 
 #include <cstdint>
+#include <cstring>
 #include <string>
 
 #include "orca_step_small.cuh"
 
 namespace orca {
 
-struct GridScratch {
-  int dummy = 0;
+struct GridParams {
+  float origin_x, origin_y, inv_cell;
+  int W, H;    // cells per env
+  int ncells;  // E * W * H
 };
 
-inline void grid_free(GridScratch&) {}
+#if defined(__CUDACC__)
+struct GridScratch {
+  int T = 0;          // agents covered by the allocation
+  int cap_cells = 0;  // capacity of the cell arrays
+  float2* sorted_pos = nullptr;
+  float2* sorted_vel = nullptr;
+  int* sorted_idx = nullptr;
+  int* key = nullptr;
+  int* slot = nullptr;
+  int* cell_count = nullptr;  // [cap_cells + 1]
+  int* cell_start = nullptr;  // [cap_cells + 1]
+  int* block_sums = nullptr;  // [scan blocks + 1]
+  int* bounds = nullptr;      // 4 order-preserving ints: min x, min y, max x, max y
+  GridParams* params = nullptr;
+};
 
-inline int launch_grid_step(GridScratch&, const StepArgs&, int, cudaStream_t, int64_t*, std::string* err) {
-  *err = "agents_per_env > 256 needs the uniform-grid pipeline (not built yet)";
+inline void grid_free(GridScratch& g) {
+  cudaFree(g.sorted_pos);
+  cudaFree(g.sorted_vel);
+  cudaFree(g.sorted_idx);
+  cudaFree(g.key);
+  cudaFree(g.slot);
+  cudaFree(g.cell_count);
+  cudaFree(g.cell_start);
+  cudaFree(g.block_sums);
+  cudaFree(g.bounds);
+  cudaFree(g.params);
+  g = GridScratch();
+}
+#endif
+
+// Candidates of an agent = agents in the 3 x 3 cells around it, read from the cell-sorted
+// snapshot.  Entries are identified by their sorted slot; `orig` maps a slot to the agent id.
+struct GridSource {
+  const float2* spos;
+  const float2* svel;
+  const int* orig;
+  const int* cell_start;
+  GridParams gp;
+  int env;     // env of the agent
+  int env_n0;  // global id of the env's first agent
+  int self;    // sorted slot of the agent itself
+
+  struct Before {
+    const int* orig;
+    ORCA_HD bool operator()(int a, int b) const { return b >= 0 && ORCA_LDG(&orig[a]) < ORCA_LDG(&orig[b]); }
+  };
+
+  ORCA_HD static int cell_coord(float x, float origin, float inv_cell, int n) {
+    int c = (int)floorf((x - origin) * inv_cell);
+    c = c < 0 ? 0 : c;
+    return c >= n ? n - 1 : c;
+  }
+
+  template <class NK>
+  ORCA_HD void gather(NK& nk, float2 p) const {
+    const int cx = cell_coord(p.x, gp.origin_x, gp.inv_cell, gp.W);
+    const int cy = cell_coord(p.y, gp.origin_y, gp.inv_cell, gp.H);
+    const int base = env * gp.W * gp.H;
+    Before before;
+    before.orig = orig;
+    const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < gp.W ? cx + 1 : gp.W - 1;
+    for (int yy = (cy > 0 ? cy - 1 : 0); yy <= (cy + 1 < gp.H ? cy + 1 : gp.H - 1); ++yy) {
+      // the cells (x0..x1, yy) are consecutive keys: one contiguous range of the sorted arrays
+      const int first = ORCA_LDG(&cell_start[base + yy * gp.W + x0]);
+      const int last = ORCA_LDG(&cell_start[base + yy * gp.W + x1 + 1]);
+      for (int q = first; q < last; ++q) {
+        if (q == self) continue;
+        const float2 o = ORCA_LDG(&spos[q]);
+        nk.offer_ranked(abs_sq(sub(p, o)), q, before);
+      }
+    }
+  }
+  ORCA_HD float2 pos(int q) const { return ORCA_LDG(&spos[q]); }
+  ORCA_HD float2 vel(int q) const { return ORCA_LDG(&svel[q]); }
+  ORCA_HD int local_id(int q) const { return ORCA_LDG(&orig[q]) - env_n0; }
+};
+
+#if defined(__CUDACC__)
+
+// order-preserving float <-> int mapping for atomicMin / atomicMax
+__device__ __forceinline__ int float_to_ordered(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void grid_reset_kernel(int* bounds) {
+  bounds[0] = bounds[1] = 0x7fffffff;
+  bounds[2] = bounds[3] = (int)0x80000000;
+}
+
+__global__ void __launch_bounds__(256) grid_bounds_kernel(const float2* __restrict__ pos, int T, int* bounds) {
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
+    const float2 p = pos[i];
+    if (isfinite(p.x) && isfinite(p.y)) {
+      mnx = fminf(mnx, p.x);
+      mny = fminf(mny, p.y);
+      mxx = fmaxf(mxx, p.x);
+      mxy = fmaxf(mxy, p.y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&bounds[0], float_to_ordered(mnx));
+    atomicMin(&bounds[1], float_to_ordered(mny));
+    atomicMax(&bounds[2], float_to_ordered(mxx));
+    atomicMax(&bounds[3], float_to_ordered(mxy));
+  }
+}
+
+// One thread: cell size = neighbor_dist, enlarged if the box would need more cells than allocated.
+__global__ void grid_params_kernel(const int* bounds, float neighbor_dist, int E, int cap_cells, GridParams* out) {
+  float mnx = ordered_to_float(bounds[0]), mny = ordered_to_float(bounds[1]);
+  float mxx = ordered_to_float(bounds[2]), mxy = ordered_to_float(bounds[3]);
+  if (!(mnx <= mxx) || !(mny <= mxy)) {
+    mnx = mny = 0.f;
+    mxx = mxy = 0.f;
+  }
+  float cell = neighbor_dist > 0.f ? neighbor_dist : 1.f;
+  int W, H;
+  for (;;) {
+    const float fw = floorf((mxx - mnx) / cell) + 1.f, fh = floorf((mxy - mny) / cell) + 1.f;
+    if (fw * fh * (float)E <= (float)cap_cells && fw < 1.0e9f && fh < 1.0e9f) {
+      W = (int)fw;
+      H = (int)fh;
+      break;
+    }
+    cell *= 1.5f;
+  }
+  out->origin_x = mnx;
+  out->origin_y = mny;
+  out->inv_cell = 1.0f / cell;
+  out->W = W;
+  out->H = H;
+  out->ncells = E * W * H;
+}
+
+__global__ void __launch_bounds__(256) grid_count_kernel(const float2* __restrict__ pos, int T, int N,
+                                                         const GridParams* __restrict__ gpp, int* cell_count,
+                                                         int* __restrict__ key, int* __restrict__ slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const GridParams gp = *gpp;
+  const float2 p = pos[i];
+  const int cx = GridSource::cell_coord(p.x, gp.origin_x, gp.inv_cell, gp.W);
+  const int cy = GridSource::cell_coord(p.y, gp.origin_y, gp.inv_cell, gp.H);
+  const int k = (i / N) * gp.W * gp.H + cy * gp.W + cx;
+  key[i] = k;
+  slot[i] = atomicAdd(&cell_count[k], 1);
+}
+
+// ---- exclusive scan of cell_count[0 .. ncells] into cell_start (ncells + 1 entries) -----------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;  // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int warp_sums[kScanThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < kScanThreads / 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane < kScanThreads / 32) warp_sums[lane] = w;
+  }
+  __syncthreads();
+  const int warp_off = warp > 0 ? warp_sums[warp - 1] : 0;
+  *total = warp_sums[kScanThreads / 32 - 1];
+  __syncthreads();
+  return warp_off + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) grid_scan_partial_kernel(const int* __restrict__ cnt,
+                                                                         const GridParams* __restrict__ gpp,
+                                                                         int* __restrict__ block_sums) {
+  const int n = gpp->ncells;
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  if (blockIdx.x * kScanTile >= n) return;
+  int s = 0;
+#pragma unroll
+  for (int t = 0; t < kScanItems; ++t) s += (base + t < n) ? cnt[base + t] : 0;
+  int total;
+  block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) grid_scan_sums_kernel(int* block_sums,
+                                                                      const GridParams* __restrict__ gpp) {
+  // single block: exclusive scan of the per-tile totals, in chunks of kScanThreads
+  const int nb = (gpp->ncells + kScanTile - 1) / kScanTile;
+  int carry = 0;
+  for (int c0 = 0; c0 < nb; c0 += kScanThreads) {
+    const int i = c0 + threadIdx.x;
+    const int v = i < nb ? block_sums[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, &total);
+    if (i < nb) block_sums[i] = carry + ex;
+    carry += total;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) grid_scan_final_kernel(const int* __restrict__ cnt,
+                                                                       const GridParams* __restrict__ gpp,
+                                                                       const int* __restrict__ block_sums,
+                                                                       int* __restrict__ start) {
+  const int n = gpp->ncells;
+  if (blockIdx.x * kScanTile >= n) return;
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+#pragma unroll
+  for (int t = 0; t < kScanItems; ++t) {
+    v[t] = (base + t < n) ? cnt[base + t] : 0;
+    s += v[t];
+  }
+  int total;
+  int off = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int t = 0; t < kScanItems; ++t) {
+    if (base + t < n) start[base + t] = off;
+    off += v[t];
+    if (base + t == n - 1) start[n] = off;  // sentinel: total agent count
+  }
+}
+
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const float2* __restrict__ pos, const float2* __restrict__ vel,
+                                                           int T, const int* __restrict__ key, const int* __restrict__ slot,
+                                                           const int* __restrict__ cell_start, float2* __restrict__ spos,
+                                                           float2* __restrict__ svel, int* __restrict__ sidx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const int j = cell_start[key[i]] + slot[i];
+  spos[j] = pos[i];
+  svel[j] = vel[i];
+  sidx[j] = i;
+}
+
+// G6: the fused step over the cell-sorted order.  Thread j handles the agent in sorted slot j, so a
+// warp's agents share cells (coherent candidate loops, cache-friendly reads).
+template <int K, bool KFULL, int POLICY>
+__global__ void __launch_bounds__(128, 6) step_grid_kernel(const StepArgs a, const float2* __restrict__ spos,
+                                                           const float2* __restrict__ svel, const int* __restrict__ sidx,
+                                                           const int* __restrict__ cell_start,
+                                                           const GridParams* __restrict__ gpp) {
+  extern __shared__ float4 smem4[];
+  const int T = a.E * a.N;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = j < T;
+  const unsigned warp_mask = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
+  const int g = sidx[j];
+  const int env = g / a.N;
+  const int la = g - env * a.N;
+  const int estep = (a.env_step != nullptr) ? a.env_step[env] : 0;
+  GridSource src;
+  src.spos = spos;
+  src.svel = svel;
+  src.orig = sidx;
+  src.cell_start = cell_start;
+  src.gp = *gpp;
+  src.env = env;
+  src.env_n0 = env * a.N;
+  src.self = j;
+  Lines L;
+  L.base = smem4 + threadIdx.x;
+  L.stride = blockDim.x;
+  agent_step_body<K, KFULL, POLICY>(a, env, la, g, spos[j], svel[j], estep, src, L, warp_mask);
+}
+
+// env_step counters are bumped by a separate tiny kernel in the grid path: an env spans many
+// blocks, so no thread of the step kernel may write the counter its siblings still read.
+__global__ void grid_bump_env_step_kernel(int* env_step, int E) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) env_step[e] += 1;
+}
+
+#define ORCA_GRID_TRY(expr)                                                         \
+  do {                                                                              \
+    cudaError_t e_ = (expr);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      *err = std::string(#expr) + " failed: " + cudaGetErrorString(e_);             \
+      return -2;                                                                    \
+    }                                                                               \
+  } while (0)
+
+inline int grid_ensure(GridScratch& G, const StepArgs& a, cudaStream_t st, std::string* err) {
+  const int T = a.E * a.N;
+  if (G.T == T && G.sorted_pos != nullptr) return 0;
+  grid_free(G);
+  // size the cell arrays from the current extent of the world (one host sync, first call only)
+  ORCA_GRID_TRY(cudaMalloc(&G.bounds, 4 * sizeof(int)));
+  ORCA_GRID_TRY(cudaMalloc(&G.params, sizeof(GridParams)));
+  grid_reset_kernel<<<1, 1, 0, st>>>(G.bounds);
+  grid_bounds_kernel<<<148 * 4, 256, 0, st>>>(a.pos, T, G.bounds);
+  int hb[4];
+  ORCA_GRID_TRY(cudaMemcpyAsync(hb, G.bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  ORCA_GRID_TRY(cudaStreamSynchronize(st));
+  auto dec = [](int i) {
+    const int b = i >= 0 ? i : i ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+  };
+  const float cell = a.nd_sq > 0.f ? sqrtf(a.nd_sq) : 1.f;
+  double w = (double)dec(hb[2]) - (double)dec(hb[0]), h = (double)dec(hb[3]) - (double)dec(hb[1]);
+  if (!(w >= 0) || !(h >= 0)) w = h = 0;
+  // room for the world to spread to ~2x its current side before the cell size has to grow
+  double cells = (2.0 * w / cell + 2.0) * (2.0 * h / cell + 2.0) * (double)a.E;
+  if (cells < 1024) cells = 1024;
+  if (cells > 1.6e7) cells = 1.6e7;
+  G.cap_cells = (int)cells;
+  G.T = T;
+  ORCA_GRID_TRY(cudaMalloc(&G.sorted_pos, (size_t)T * sizeof(float2)));
+  ORCA_GRID_TRY(cudaMalloc(&G.sorted_vel, (size_t)T * sizeof(float2)));
+  ORCA_GRID_TRY(cudaMalloc(&G.sorted_idx, (size_t)T * sizeof(int)));
+  ORCA_GRID_TRY(cudaMalloc(&G.key, (size_t)T * sizeof(int)));
+  ORCA_GRID_TRY(cudaMalloc(&G.slot, (size_t)T * sizeof(int)));
+  ORCA_GRID_TRY(cudaMalloc(&G.cell_count, ((size_t)G.cap_cells + 1) * sizeof(int)));
+  ORCA_GRID_TRY(cudaMalloc(&G.cell_start, ((size_t)G.cap_cells + 1) * sizeof(int)));
+  ORCA_GRID_TRY(cudaMalloc(&G.block_sums, ((size_t)G.cap_cells / kScanTile + 2) * sizeof(int)));
+  return 0;
+}
+
+template <int K, bool KFULL, int POLICY>
+int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* launches, std::string* err) {
+  const int T = a.E * a.N;
+  const int rc = grid_ensure(G, a, st, err);
+  if (rc != 0) return rc;
+  const int tpb = 256;
+  const int nb_agents = (T + tpb - 1) / tpb;
+  grid_reset_kernel<<<1, 1, 0, st>>>(G.bounds);
+  grid_bounds_kernel<<<148 * 4, 256, 0, st>>>(a.pos, T, G.bounds);
+  grid_params_kernel<<<1, 1, 0, st>>>(G.bounds, sqrtf(a.nd_sq), a.E, G.cap_cells, G.params);
+  ORCA_GRID_TRY(cudaMemsetAsync(G.cell_count, 0, ((size_t)G.cap_cells + 1) * sizeof(int), st));
+  grid_count_kernel<<<nb_agents, tpb, 0, st>>>(a.pos, T, a.N, G.params, G.cell_count, G.key, G.slot);
+  const int scan_blocks = (G.cap_cells + kScanTile - 1) / kScanTile;
+  grid_scan_partial_kernel<<<scan_blocks, kScanThreads, 0, st>>>(G.cell_count, G.params, G.block_sums);
+  grid_scan_sums_kernel<<<1, kScanThreads, 0, st>>>(G.block_sums, G.params);
+  grid_scan_final_kernel<<<scan_blocks, kScanThreads, 0, st>>>(G.cell_count, G.params, G.block_sums, G.cell_start);
+  grid_scatter_kernel<<<nb_agents, tpb, 0, st>>>(a.pos, a.vel, T, G.key, G.slot, G.cell_start, G.sorted_pos,
+                                                 G.sorted_vel, G.sorted_idx);
+  StepArgs args = a;
+  int* env_step = args.env_step;
+  // the step kernel only READS the counters in this path (see grid_bump_env_step_kernel)
+  const int stpb = 128;
+  const size_t smem = (size_t)stpb * (K + ORCA_MAX_OBST_LINES) * 16;
+  auto kern = step_grid_kernel<K, KFULL, POLICY>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ORCA_GRID_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  args.grid_path = 1;
+  kern<<<(T + stpb - 1) / stpb, stpb, smem, st>>>(args, G.sorted_pos, G.sorted_vel, G.sorted_idx, G.cell_start, G.params);
+  int n_launch = 9;
+  if (env_step != nullptr && !a.neighbors_only) {
+    grid_bump_env_step_kernel<<<(a.E + 255) / 256, 256, 0, st>>>(env_step, a.E);
+    ++n_launch;
+  }
+  ORCA_GRID_TRY(cudaGetLastError());
+  *launches += n_launch;
+  return 0;
+}
+
+template <int K, bool KFULL>
+int launch_grid_k(GridScratch& G, const StepArgs& a, int policy, cudaStream_t st, int64_t* launches, std::string* err) {
+  switch (policy) {
+    case POLICY_EXTERNAL:
+      return launch_grid_kp<K, KFULL, POLICY_EXTERNAL>(G, a, st, launches, err);
+    case POLICY_GOAL:
+      return launch_grid_kp<K, KFULL, POLICY_GOAL>(G, a, st, launches, err);
+    case POLICY_RL:
+      return launch_grid_kp<K, KFULL, POLICY_RL>(G, a, st, launches, err);
+    case POLICY_ALAN:
+      return launch_grid_kp<K, KFULL, POLICY_ALAN>(G, a, st, launches, err);
+    default:
+      *err = "unknown policy";
+      return -1;
+  }
+}
+
+inline int launch_grid_step(GridScratch& G, const StepArgs& a, int policy, cudaStream_t st, int64_t* launches,
+                            std::string* err) {
+  if (a.k == 5) return launch_grid_k<5, true>(G, a, policy, st, launches, err);
+  if (a.k == 10) return launch_grid_k<10, true>(G, a, policy, st, launches, err);
+  if (a.k <= 16) return launch_grid_k<16, false>(G, a, policy, st, launches, err);
+  *err = "max_neighbors > 16 is not supported";
   return -3;
 }
+
+#endif  // __CUDACC__
 
 }  // namespace orca

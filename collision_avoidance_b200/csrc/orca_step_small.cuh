@@ -80,6 +80,9 @@ struct StepArgs {
   int vert_stride;       // per-env table stride (0 when shared)
   // 1: stop after the neighbor search (orca_neighbors parity hook)
   int neighbors_only;
+  // 1: uniform-grid path; an env spans several blocks, so its step counter is bumped by a
+  // separate kernel instead of by the env's first agent
+  int grid_path;
 };
 
 struct LocalLines {  // LP3 scratch in local memory (rarely touched; lives in L1)
@@ -93,6 +96,26 @@ struct LocalLines {  // LP3 scratch in local memory (rarely touched; lives in L1
     v.w = dir.y;
     base[i] = v;
   }
+};
+
+// Where an agent's neighbor candidates come from.  TileSource: the pre-step snapshot of the
+// agent's own env in shared memory, candidates = every other agent of the env in id order.
+struct TileSource {
+  const float2* env_pos;
+  const float2* env_vel;
+  int n;
+  int self;
+  template <class NK>
+  ORCA_HD void gather(NK& nk, float2 p) const {
+    for (int j = 0; j < n; ++j) {
+      if (j == self) continue;
+      const float2 q = env_pos[j];
+      nk.offer(abs_sq(sub(p, q)), j);
+    }
+  }
+  ORCA_HD float2 pos(int q) const { return env_pos[q]; }
+  ORCA_HD float2 vel(int q) const { return env_vel[q]; }
+  ORCA_HD int local_id(int q) const { return q; }
 };
 
 // atomics: device atomics in the kernels, plain adds in the single-threaded host emulation
@@ -122,14 +145,12 @@ ORCA_HD void counter_inc(int* c) {
 #endif
 }
 
-// Everything one agent does in one fused step.  `env_pos` / `env_vel` are the PRE-step
-// snapshot of the agent's env (shared memory in the kernel), `L` its private line storage,
+// Everything one agent does in one fused step.  `src` yields the PRE-step state of the other
+// agents (shared-memory tile or uniform-grid cells), `L` is the agent's private line storage,
 // (p, v) its own pre-step state, `estep` the env's step counter before this step.
-template <int K, bool KFULL, int POLICY>
+template <int K, bool KFULL, int POLICY, class Src>
 ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, const int g, float2 p, float2 v,
-                             const int estep, const float2* env_pos, const float2* env_vel, const Lines L,
-                             const unsigned warp_mask) {
-  const int N = a.N;
+                             const int estep, const Src& src, const Lines L, const unsigned warp_mask) {
 
   // ---------------- preferred velocity (policy) ----------------
   float2 gdir = v2(0.f, 0.f);
@@ -197,20 +218,14 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
 
   NearestK<K, KFULL> nk;
   nk.init(a.k, a.nd_sq);
-  {
-    for (int j = 0; j < N; ++j) {
-      if (j == la) continue;
-      const float2 q = env_pos[j];
-      nk.offer(abs_sq(sub(p, q)), j);
-    }
-  }
+  src.gather(nk, p);
 
   if (a.nbr_idx != nullptr) {
     int c = 0;
 #pragma unroll
     for (int s = 0; s < K; ++s) {
       if (s < a.k) {
-        a.nbr_idx[(size_t)g * a.k + s] = nk.id[s];
+        a.nbr_idx[(size_t)g * a.k + s] = (nk.id[s] >= 0) ? src.local_id(nk.id[s]) : -1;
         if (a.nbr_dsq != nullptr) a.nbr_dsq[(size_t)g * a.k + s] = (nk.id[s] >= 0) ? nk.d[s] : 0.f;
         c += (nk.id[s] >= 0) ? 1 : 0;
       }
@@ -235,7 +250,7 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
       const int j = nk.id[s];
       if (j >= 0) {
         bool hit;
-        const float4 ln = agent_line(p, v, env_pos[j], env_vel[j], cr, a.inv_th, a.inv_dt, &hit);
+        const float4 ln = agent_line(p, v, src.pos(j), src.vel(j), cr, a.inv_th, a.inv_dt, &hit);
         L.base[n * L.stride] = ln;
         ++n;
         collisions += hit ? 1u : 0u;
@@ -304,7 +319,7 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
       }
     }
   }
-  if (a.env_step != nullptr && la == 0) a.env_step[env] = estep + 1;
+  if (a.env_step != nullptr && la == 0 && !a.grid_path) a.env_step[env] = estep + 1;
   stat_add_u64(a.stats, STAT_COLLISIONS, (unsigned long long)collisions);
   stat_add_u64(a.stats, STAT_OVERFLOW, overflow ? 1ull : 0ull);
 }
@@ -350,7 +365,12 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   Lines L;
   L.base = s_lines + tid;
   L.stride = tpb;
-  agent_step_body<K, KFULL, POLICY>(a, env, la, g, p, v, estep, s_pos + le * N, s_vel + le * N, L, warp_mask);
+  TileSource src;
+  src.env_pos = s_pos + le * N;
+  src.env_vel = s_vel + le * N;
+  src.n = N;
+  src.self = la;
+  agent_step_body<K, KFULL, POLICY>(a, env, la, g, p, v, estep, src, L, warp_mask);
 }
 
 #endif  // __CUDACC__

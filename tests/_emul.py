@@ -32,7 +32,7 @@ class StepArgs(ctypes.Structure):
         ("nbr_idx", c_p), ("nbr_dsq", c_p), ("nbr_cnt", c_p), ("onbr_idx", c_p), ("onbr_cnt", c_p),
         ("stats", c_p),
         ("vert_pd", c_p), ("vert_link", c_p), ("bsp", c_p), ("bsp_seg", c_p), ("env_nodes", c_p),
-        ("shared_nodes", c_i), ("vert_stride", c_i), ("neighbors_only", c_i),
+        ("shared_nodes", c_i), ("vert_stride", c_i), ("neighbors_only", c_i), ("grid_path", c_i),
     ]
 
 
@@ -63,6 +63,8 @@ def lib():
         L.emul_observe.argtypes = [ctypes.POINTER(ObsArgs), c_f, c_f]
         L.emul_step.argtypes = [ctypes.POINTER(StepArgs), c_i]
         L.emul_step.restype = c_i
+        L.emul_step_grid.argtypes = [ctypes.POINTER(StepArgs), c_i]
+        L.emul_step_grid.restype = c_i
         L.emul_build_world.restype = c_i
         L.emul_philox_uniform.restype = c_f
         L.emul_philox_uniform.argtypes = [ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint]
@@ -99,7 +101,7 @@ class World:
 def emul_step(params, pos, vel, *, policy=0, pref=None, goal=None, goal2=None, world=None, action_theta=None,
               rl_scale=0.3, done_x=2.0, alan_w=None, alan_actions=None, alan_uniform=None, alan_window=121,
               alan_gamma=0.6, alan_temp=0.2, seed=0, done_mode=0, agent_done=None, arrival=None, env_step=None,
-              env_done_cnt=None, want_neighbors=False, neighbors_only=False, stats=None):
+              env_done_cnt=None, want_neighbors=False, neighbors_only=False, stats=None, grid=False):
     """Run one fused step on host arrays, in place.  pos/vel: float32 [E, N, 2].
     Returns dict with optional outputs (reward, action, nbr_idx, nbr_cnt, ...)."""
     E, N = pos.shape[0], pos.shape[1]
@@ -148,7 +150,7 @@ def emul_step(params, pos, vel, *, policy=0, pref=None, goal=None, goal2=None, w
         a.vert_pd, a.vert_link, a.bsp, a.bsp_seg = _ptr(world.pd), _ptr(world.link), _ptr(world.bsp), _ptr(world.seg)
         a.shared_nodes, a.vert_stride = world.nv, 0
     a.neighbors_only = 1 if neighbors_only else 0
-    rc = lib().emul_step(ctypes.byref(a), policy)
+    rc = lib().emul_step_grid(ctypes.byref(a), policy) if grid else lib().emul_step(ctypes.byref(a), policy)
     assert rc == 0
     return out
 

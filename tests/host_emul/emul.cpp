@@ -14,6 +14,7 @@ static inline void sincosf_(float x, float* s, float* c) { *s = sinf(x); *c = co
 #include "../../collision_avoidance_b200/csrc/obstacle_world.h"
 #include "../../collision_avoidance_b200/csrc/orca_step_small.cuh"
 #include "../../collision_avoidance_b200/csrc/orca_obs.cuh"
+#include "../../collision_avoidance_b200/csrc/orca_grid.cuh"
 
 namespace {
 template <int K, bool KFULL>
@@ -32,14 +33,70 @@ void run_k(const orca::StepArgs& a, int policy) {
       L.base = lines.data();
       L.stride = 1;
       const int g = e * N + i;
+      orca::TileSource src;
+      src.env_pos = spos.data();
+      src.env_vel = svel.data();
+      src.n = N;
+      src.self = i;
       switch (policy) {
-        case 0: orca::agent_step_body<K, KFULL, 0>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L, 0xffffffffu); break;
-        case 1: orca::agent_step_body<K, KFULL, 1>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L, 0xffffffffu); break;
-        case 2: orca::agent_step_body<K, KFULL, 2>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L, 0xffffffffu); break;
-        default: orca::agent_step_body<K, KFULL, 3>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, spos.data(), svel.data(), L, 0xffffffffu); break;
+        case 0: orca::agent_step_body<K, KFULL, 0>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, src, L, 0xffffffffu); break;
+        case 1: orca::agent_step_body<K, KFULL, 1>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, src, L, 0xffffffffu); break;
+        case 2: orca::agent_step_body<K, KFULL, 2>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, src, L, 0xffffffffu); break;
+        default: orca::agent_step_body<K, KFULL, 3>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, src, L, 0xffffffffu); break;
       }
     }
   }
+}
+// Host twin of the uniform-grid pipeline (G1-G6 of orca_grid.cuh): bounds, cell keys, counting
+// sort (serial, so slots inside a cell follow agent order -- any order is legal), then the same
+// agent_step_body with a GridSource.
+template <int K, bool KFULL>
+void run_grid_k(const orca::StepArgs& a0, int policy) {
+  orca::StepArgs a = a0;
+  a.grid_path = 1;
+  const int E = a.E, N = a.N, T = E * N;
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = 0; i < T; ++i) {
+    mnx = std::fmin(mnx, a.pos[i].x); mny = std::fmin(mny, a.pos[i].y);
+    mxx = std::fmax(mxx, a.pos[i].x); mxy = std::fmax(mxy, a.pos[i].y);
+  }
+  orca::GridParams gp;
+  const float cell = std::sqrt(a.nd_sq);
+  gp.origin_x = mnx; gp.origin_y = mny; gp.inv_cell = 1.0f / cell;
+  gp.W = (int)(std::floor((mxx - mnx) / cell) + 1.f);
+  gp.H = (int)(std::floor((mxy - mny) / cell) + 1.f);
+  gp.ncells = E * gp.W * gp.H;
+  std::vector<int> key((size_t)T), start((size_t)gp.ncells + 1, 0), sidx((size_t)T);
+  for (int i = 0; i < T; ++i) {
+    const int cx = orca::GridSource::cell_coord(a.pos[i].x, gp.origin_x, gp.inv_cell, gp.W);
+    const int cy = orca::GridSource::cell_coord(a.pos[i].y, gp.origin_y, gp.inv_cell, gp.H);
+    key[(size_t)i] = (i / N) * gp.W * gp.H + cy * gp.W + cx;
+    start[(size_t)key[(size_t)i] + 1]++;
+  }
+  for (int c = 0; c < gp.ncells; ++c) start[(size_t)c + 1] += start[(size_t)c];
+  std::vector<int> fill(start.begin(), start.end() - 1);
+  // reversed agent order inside each cell on purpose: the result must not depend on it
+  for (int i = T - 1; i >= 0; --i) sidx[(size_t)fill[(size_t)key[(size_t)i]]++] = i;
+  std::vector<float2> spos((size_t)T), svel((size_t)T);
+  for (int j = 0; j < T; ++j) { spos[(size_t)j] = a.pos[sidx[(size_t)j]]; svel[(size_t)j] = a.vel[sidx[(size_t)j]]; }
+  std::vector<int> estep0((size_t)E, 0);
+  if (a.env_step) for (int e = 0; e < E; ++e) estep0[(size_t)e] = a.env_step[e];
+  std::vector<float4> lines((size_t)(K + ORCA_MAX_OBST_LINES));
+  for (int j = 0; j < T; ++j) {
+    const int g = sidx[(size_t)j], env = g / N, la = g - env * N;
+    orca::GridSource src;
+    src.spos = spos.data(); src.svel = svel.data(); src.orig = sidx.data(); src.cell_start = start.data();
+    src.gp = gp; src.env = env; src.env_n0 = env * N; src.self = j;
+    orca::Lines L; L.base = lines.data(); L.stride = 1;
+    const int es = estep0[(size_t)env];
+    switch (policy) {
+      case 0: orca::agent_step_body<K, KFULL, 0>(a, env, la, g, spos[(size_t)j], svel[(size_t)j], es, src, L, 0xffffffffu); break;
+      case 1: orca::agent_step_body<K, KFULL, 1>(a, env, la, g, spos[(size_t)j], svel[(size_t)j], es, src, L, 0xffffffffu); break;
+      case 2: orca::agent_step_body<K, KFULL, 2>(a, env, la, g, spos[(size_t)j], svel[(size_t)j], es, src, L, 0xffffffffu); break;
+      default: orca::agent_step_body<K, KFULL, 3>(a, env, la, g, spos[(size_t)j], svel[(size_t)j], es, src, L, 0xffffffffu); break;
+    }
+  }
+  if (a.env_step && !a.neighbors_only) for (int e = 0; e < E; ++e) a.env_step[e] += 1;
 }
 }  // namespace
 
@@ -96,6 +153,14 @@ int emul_observe(orca::ObsArgs* a, float neighbor_dist, float radius) {
   return 0;
 }
 int emul_obsargs_size() { return (int)sizeof(orca::ObsArgs); }
+
+int emul_step_grid(const orca::StepArgs* a, int policy) {
+  if (a->k == 5) run_grid_k<5, true>(*a, policy);
+  else if (a->k == 10) run_grid_k<10, true>(*a, policy);
+  else if (a->k <= 16) run_grid_k<16, false>(*a, policy);
+  else return -1;
+  return 0;
+}
 
 int emul_stepargs_size() { return (int)sizeof(orca::StepArgs); }
 
