@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -46,6 +47,7 @@ struct OrcaSim {
   OrcaParams p{};
   int device = 0;
   int E = 0, N = 0;
+  int grid_min_agents = 257;  // worlds with at least this many agents use the uniform-grid pipeline
   // obstacle world(s)
   std::vector<orca_host::ObstacleTables> worlds;  // 1 (shared) or E
   bool per_env = false;
@@ -121,11 +123,11 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   orca::StepArgs args = a;
   args.envs_per_block = tpb / N;
   const int blocks = (s->E + args.envs_per_block - 1) / args.envs_per_block;
-  const size_t smem = (size_t)tpb * (16 + (size_t)(K + ORCA_MAX_OBST_LINES) * 16);
+  const size_t smem = orca::step_smem_bytes(K, tpb, true);
   auto kern = orca::step_small_kernel<K, KFULL, POLICY>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * (16 + (K + ORCA_MAX_OBST_LINES) * 16)));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::step_smem_bytes(K, 256, true)));
     attr_set = true;
   }
   kern<<<blocks, tpb, smem, st>>>(args);
@@ -151,7 +153,7 @@ int launch_small_k(OrcaSim* s, const orca::StepArgs& a, int policy, cudaStream_t
 }
 
 int launch_step(OrcaSim* s, const orca::StepArgs& a, int policy, cudaStream_t st) {
-  if (s->N > 256) {
+  if (s->N >= s->grid_min_agents) {
     return orca::launch_grid_step(s->grid, a, policy, st, &s->launches, &g_last_error);
   }
   const int k = s->p.max_neighbors;
@@ -196,6 +198,11 @@ int orca_create(const OrcaParams* params, int device, int num_envs, int agents_p
   s->device = device;
   s->E = num_envs;
   s->N = agents_per_env;
+  // tuning knob: the shared-memory tile path covers at most 256 agents per env
+  if (const char* e = std::getenv("ORCA_B200_GRID_MIN_AGENTS")) {
+    const int v = std::atoi(e);
+    if (v >= 1 && v <= 257) s->grid_min_agents = v;
+  }
   *out = s;
   return ORCA_OK;
 }

@@ -38,6 +38,12 @@ struct GridParams {
   int ncells;  // E * W * H
 };
 
+// Cell size: neighbor_dist plus 0.1 %.  The margin absorbs the rounding of (x - origin) * inv_cell
+// (about 1.2e-7 relative, i.e. < 1e-3 cells up to ~8000 cells per side), so two agents closer than
+// neighbor_dist always land at most one cell apart.  Exactly neighbor_dist (inv_cell = 0.2f is a
+// hair above 1/5) would let pairs at 4.9999999 fall two cells apart.
+ORCA_HD float grid_cell_size(float neighbor_dist) { return (neighbor_dist > 0.f ? neighbor_dist : 1.f) * 1.001f; }
+
 #if defined(__CUDACC__)
 struct GridScratch {
   int T = 0;          // agents covered by the allocation
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(256) grid_bounds_kernel(const float2* __restri
   }
 }
 
-// One thread: cell size = neighbor_dist, enlarged if the box would need more cells than allocated.
+// One thread: grid origin / dims; the cell is enlarged if the box would need more cells than allocated.
 __global__ void grid_params_kernel(const int* bounds, float neighbor_dist, int E, int cap_cells, GridParams* out) {
   float mnx = ordered_to_float(bounds[0]), mny = ordered_to_float(bounds[1]);
   float mxx = ordered_to_float(bounds[2]), mxy = ordered_to_float(bounds[3]);
@@ -164,7 +170,7 @@ __global__ void grid_params_kernel(const int* bounds, float neighbor_dist, int E
     mnx = mny = 0.f;
     mxx = mxy = 0.f;
   }
-  float cell = neighbor_dist > 0.f ? neighbor_dist : 1.f;
+  float cell = grid_cell_size(neighbor_dist);
   int W, H;
   for (;;) {
     const float fw = floorf((mxx - mnx) / cell) + 1.f, fh = floorf((mxy - mny) / cell) + 1.f;
@@ -302,28 +308,49 @@ __global__ void __launch_bounds__(128, 6) step_grid_kernel(const StepArgs a, con
                                                            const int* __restrict__ cell_start,
                                                            const GridParams* __restrict__ gpp) {
   extern __shared__ float4 smem4[];
+  const int tpb = blockDim.x;
+  float4* s_lines = smem4;
+  float2* s_nv = reinterpret_cast<float2*>(s_lines + (K + ORCA_MAX_OBST_LINES) * tpb);
+  int* s_meta = reinterpret_cast<int*>(s_nv + tpb);
+  int* s_warp_cnt = s_meta + tpb;
+  unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_warp_cnt + 32);
   const int T = a.E * a.N;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = j < T;
   const unsigned warp_mask = __ballot_sync(0xffffffffu, valid);
-  if (!valid) return;
-  const int g = sidx[j];
-  const int env = g / a.N;
-  const int la = g - env * a.N;
-  const int estep = (a.env_step != nullptr) ? a.env_step[env] : 0;
-  GridSource src;
-  src.spos = spos;
-  src.svel = svel;
-  src.orig = sidx;
-  src.cell_start = cell_start;
-  src.gp = *gpp;
-  src.env = env;
-  src.env_n0 = env * a.N;
-  src.self = j;
-  Lines L;
-  L.base = smem4 + threadIdx.x;
-  L.stride = blockDim.x;
-  agent_step_body<K, KFULL, POLICY>(a, env, la, g, spos[j], svel[j], estep, src, L, warp_mask);
+  AgentCarry c;
+  c.p = v2(0.f, 0.f);
+  c.v = v2(0.f, 0.f);
+  c.nv = v2(0.f, 0.f);
+  c.n = c.n_obst = c.fail = 0;
+  int g = 0, env = 0, la = 0, estep = 0;
+  bool alive = valid;
+  if (valid) {
+    g = sidx[j];
+    env = g / a.N;
+    la = g - env * a.N;
+    estep = (a.env_step != nullptr) ? a.env_step[env] : 0;
+    GridSource src;
+    src.spos = spos;
+    src.svel = svel;
+    src.orig = sidx;
+    src.cell_start = cell_start;
+    src.gp = *gpp;
+    src.env = env;
+    src.env_n0 = env * a.N;
+    src.self = j;
+    Lines L;
+    L.base = s_lines + threadIdx.x;
+    L.stride = tpb;
+    c.p = spos[j];
+    c.v = svel[j];
+    alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, L, warp_mask, c);
+  }
+  if (a.neighbors_only) return;  // uniform over the grid
+  block_lp3<K>(s_lines, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);
+  if (!alive) return;
+  c.nv = s_nv[threadIdx.x];
+  agent_back<POLICY>(a, env, la, g, estep, c);
 }
 
 // env_step counters are bumped by a separate tiny kernel in the grid path: an env spans many
@@ -360,7 +387,7 @@ inline int grid_ensure(GridScratch& G, const StepArgs& a, cudaStream_t st, std::
     memcpy(&f, &b, 4);
     return f;
   };
-  const float cell = a.nd_sq > 0.f ? sqrtf(a.nd_sq) : 1.f;
+  const float cell = grid_cell_size(sqrtf(a.nd_sq));
   double w = (double)dec(hb[2]) - (double)dec(hb[0]), h = (double)dec(hb[3]) - (double)dec(hb[1]);
   if (!(w >= 0) || !(h >= 0)) w = h = 0;
   // room for the world to spread to ~2x its current side before the cell size has to grow
@@ -402,7 +429,7 @@ int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* 
   int* env_step = args.env_step;
   // the step kernel only READS the counters in this path (see grid_bump_env_step_kernel)
   const int stpb = 128;
-  const size_t smem = (size_t)stpb * (K + ORCA_MAX_OBST_LINES) * 16;
+  const size_t smem = step_smem_bytes(K, stpb, false);
   auto kern = step_grid_kernel<K, KFULL, POLICY>;
   static bool attr_set = false;
   if (!attr_set) {

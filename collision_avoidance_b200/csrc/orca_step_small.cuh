@@ -145,12 +145,27 @@ ORCA_HD void counter_inc(int* c) {
 #endif
 }
 
-// Everything one agent does in one fused step.  `src` yields the PRE-step state of the other
-// agents (shared-memory tile or uniform-grid cells), `L` is the agent's private line storage,
-// (p, v) its own pre-step state, `estep` the env's step counter before this step.
+// What an agent carries from the front half of the step (policy, neighbors, half-planes, LP2)
+// across the LP3 stage to the back half (integration, reward, bandit update, done test).
+struct AgentCarry {
+  float2 p, v;     // pre-step state
+  float2 gdir;     // unit vector to the goal (pre-step position)
+  float2 pref;     // preferred velocity handed to ORCA
+  float2 nv;       // new velocity
+  int act;         // ALAN: chosen action
+  int n, n_obst;   // ORCA lines, obstacle lines among them
+  int fail;        // LP2 failure index (== n when feasible)
+  unsigned collisions;
+  bool overflow;
+};
+
+// Front half.  `src` yields the PRE-step state of the other agents (shared-memory tile or
+// uniform-grid cells), `L` is the agent's private line storage, `estep` the env's step counter
+// before this step.  Returns false when the step ends here (neighbors-only parity hook).
 template <int K, bool KFULL, int POLICY, class Src>
-ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, const int g, float2 p, float2 v,
-                             const int estep, const Src& src, const Lines L, const unsigned warp_mask) {
+ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const int estep, const Src& src,
+                         const Lines L, const unsigned warp_mask, AgentCarry& c) {
+  const float2 p = c.p, v = c.v;
 
   // ---------------- preferred velocity (policy) ----------------
   float2 gdir = v2(0.f, 0.f);
@@ -199,6 +214,9 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
       if (a.alan_action_out != nullptr) a.alan_action_out[g] = (uint8_t)act;
     }
   }
+  c.gdir = gdir;
+  c.pref = pref;
+  c.act = act;
 
   // ---------------- neighbors ----------------
   ObstacleWorld W;
@@ -221,22 +239,22 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
   src.gather(nk, p);
 
   if (a.nbr_idx != nullptr) {
-    int c = 0;
+    int cnt = 0;
 #pragma unroll
     for (int s = 0; s < K; ++s) {
       if (s < a.k) {
         a.nbr_idx[(size_t)g * a.k + s] = (nk.id[s] >= 0) ? src.local_id(nk.id[s]) : -1;
         if (a.nbr_dsq != nullptr) a.nbr_dsq[(size_t)g * a.k + s] = (nk.id[s] >= 0) ? nk.d[s] : 0.f;
-        c += (nk.id[s] >= 0) ? 1 : 0;
+        cnt += (nk.id[s] >= 0) ? 1 : 0;
       }
     }
-    a.nbr_cnt[g] = c;
+    a.nbr_cnt[g] = cnt;
   }
   if (a.onbr_idx != nullptr) {
     for (int s = 0; s < ORCA_MAX_OBST_NEIGHBORS; ++s) a.onbr_idx[(size_t)g * ORCA_MAX_OBST_NEIGHBORS + s] = (s < ocnt) ? oid[s] : -1;
     a.onbr_cnt[g] = ocnt;
   }
-  if (a.neighbors_only) return;
+  if (a.neighbors_only) return false;
 
   // ---------------- ORCA lines ----------------
   int n_obst = 0;
@@ -257,29 +275,32 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
       }
     }
   }
+  c.n = n;
+  c.n_obst = n_obst;
+  c.collisions = collisions;
+  c.overflow = overflow;
 
-  // ---------------- linear programs ----------------
-  float2 nv;
-  const int fail = lp2(warp_mask, true, L, n, a.vmax, pref, false, nv);
-  {
-    // every lane takes part (warp-synchronous loops); only lanes whose LP2 failed do work
-    float4 proj[K + ORCA_MAX_OBST_LINES];
-    LocalLines P;
-    P.base = proj;
-    lp3(warp_mask, fail < n, L, n, n_obst, fail, a.vmax, P, nv);
-    if (fail < n) stat_add_u64(a.stats, STAT_LP3_CALLS, 1ull);
-  }
+  // ---------------- LP2 ----------------
+  c.fail = lp2(warp_mask, true, L, n, a.vmax, pref, false, c.nv);
+  return true;
+}
+
+// Back half: Agent::update + reward + bandit update + done test, with c.nv final.
+template <int POLICY>
+ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const int g, const int estep,
+                        const AgentCarry& c) {
+  if (c.fail < c.n) stat_add_u64(a.stats, STAT_LP3_CALLS, 1ull);
 
   // ---------------- integrate (Agent::update) ----------------
-  v = nv;
-  p = add(p, mul(a.dt, v));  // position += velocity * timeStep
+  const float2 v = c.nv;
+  const float2 p = add(c.p, mul(a.dt, v));  // position += velocity * timeStep
   a.pos[g] = p;
   a.vel[g] = v;
 
   // ---------------- reward / bandit update ----------------
   if (POLICY == POLICY_RL || POLICY == POLICY_ALAN) {
-    const float r_goal = dot(v, gdir);
-    const float r_polite = dot(v, pref);
+    const float r_goal = dot(v, c.gdir);
+    const float r_polite = dot(v, c.pref);
     float R;
     if (POLICY == POLICY_RL)
       R = a.rl_scale * r_goal + (1.f - a.rl_scale) * r_polite;
@@ -293,7 +314,7 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
       if (a.alan_window > 0 && ((estep + 1) % a.alan_window) == 0) {
         for (int i = 0; i < a.A; ++i) wrow[i] = 0.f;
       }
-      wrow[act] = R;
+      wrow[c.act] = R;
     }
   }
 
@@ -320,8 +341,23 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
     }
   }
   if (a.env_step != nullptr && la == 0 && !a.grid_path) a.env_step[env] = estep + 1;
-  stat_add_u64(a.stats, STAT_COLLISIONS, (unsigned long long)collisions);
-  stat_add_u64(a.stats, STAT_OVERFLOW, overflow ? 1ull : 0ull);
+  stat_add_u64(a.stats, STAT_COLLISIONS, (unsigned long long)c.collisions);
+  stat_add_u64(a.stats, STAT_OVERFLOW, c.overflow ? 1ull : 0ull);
+}
+
+// Front + LP3 + back for one agent, no work redistribution (host emulation; reference order).
+template <int K, bool KFULL, int POLICY, class Src>
+ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, const int g, float2 p, float2 v,
+                             const int estep, const Src& src, const Lines L, const unsigned warp_mask) {
+  AgentCarry c;
+  c.p = p;
+  c.v = v;
+  if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, L, warp_mask, c)) return;
+  float4 proj[K + ORCA_MAX_OBST_LINES];
+  LocalLines P;
+  P.base = proj;
+  lp3(warp_mask, c.fail < c.n, L, c.n, c.n_obst, c.fail, a.vmax, P, c.nv);
+  agent_back<POLICY>(a, env, la, g, estep, c);
 }
 
 #if defined(__CUDACC__)
@@ -334,13 +370,83 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
 #define ORCA_STEP_MIN_BLOCKS 3
 #endif
 
+// dynamic shared memory of the step kernels: [pos|vel tile (tile path only)] + lines + LP3 queue
+inline size_t step_smem_bytes(int K, int tpb, bool tile) {
+  return (size_t)tpb * ((tile ? 16 : 0) + (size_t)(K + ORCA_MAX_OBST_LINES) * 16 + 8 + 4 + 2) + 32 * 4;
+}
+
+// LP3 with block-level work compaction.  Only the agents whose LP2 was infeasible need LP3
+// (0-40 % of them, scattered over the block's warps); left in place every warp would walk the
+// LP3 loops with a few live lanes.  Instead the block builds a dense queue of those agents and
+// threads 0..count-1 each solve one of them -- the ORCA lines already live in shared memory
+// (line i of agent o at lines[i * blockDim + o]), so any thread can work on any agent.
+//   s_meta[t] = n | n_obst << 8 | fail << 16,  s_nv[t] = LP2 result in / LP3 result out.
+// Must be called by every thread of the block (it contains barriers).
+#ifndef ORCA_BLOCK_LP3
+#define ORCA_BLOCK_LP3 1
+#endif
+template <int K>
+__device__ __forceinline__ void block_lp3(float4* s_lines, int* s_meta, float2* s_nv, unsigned short* s_queue,
+                                          int* s_warp_cnt, const bool need, const AgentCarry& c, const float vmax) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+#if !ORCA_BLOCK_LP3
+  {  // in-place variant (kept for A/B measurements): every thread solves its own agent
+    Lines L;
+    L.base = s_lines + tid;
+    L.stride = blockDim.x;
+    float4 proj[K + ORCA_MAX_OBST_LINES];
+    LocalLines P;
+    P.base = proj;
+    float2 nv = c.nv;
+    lp3(0xffffffffu, need, L, c.n, c.n_obst, c.fail, vmax, P, nv);
+    s_nv[tid] = nv;
+    __syncwarp();
+    return;
+  }
+#endif
+  s_meta[tid] = c.n | (c.n_obst << 8) | (c.fail << 16);
+  s_nv[tid] = c.nv;
+  const unsigned bal = __ballot_sync(0xffffffffu, need);
+  if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  int offset = 0, total = 0;
+  for (int w = 0; w < nwarps; ++w) {
+    const int cw = s_warp_cnt[w];
+    offset += (w < warp) ? cw : 0;
+    total += cw;
+  }
+  if (need) s_queue[offset + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)tid;
+  __syncthreads();
+  if ((warp << 5) < total) {  // warp-uniform: this warp owns queue entries
+    const bool mine = tid < total;
+    const int owner = mine ? (int)s_queue[tid] : tid;
+    const int meta = s_meta[owner];
+    Lines L;
+    L.base = s_lines + owner;
+    L.stride = blockDim.x;
+    float4 proj[K + ORCA_MAX_OBST_LINES];
+    LocalLines P;
+    P.base = proj;
+    float2 nv = s_nv[owner];
+    lp3(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, P, nv);
+    if (mine) s_nv[owner] = nv;
+  }
+  __syncthreads();
+}
+
 template <int K, bool KFULL, int POLICY>
 __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) step_small_kernel(const StepArgs a) {
   extern __shared__ float4 smem4[];
   const int tpb = blockDim.x;
+  // [pos | vel] tile: 2 * tpb float2 = tpb float4 ; lines: (K + MAX_OBST_LINES) * tpb float4 ;
+  // LP3 queue: nv (tpb float2), meta (tpb int), queue (tpb u16), warp counters
   float2* s_pos = reinterpret_cast<float2*>(smem4);
   float2* s_vel = s_pos + tpb;
-  float4* s_lines = smem4 + tpb;  // after 2 * tpb float2 = tpb float4
+  float4* s_lines = smem4 + tpb;
+  float2* s_nv = reinterpret_cast<float2*>(s_lines + (K + ORCA_MAX_OBST_LINES) * tpb);
+  int* s_meta = reinterpret_cast<int*>(s_nv + tpb);
+  int* s_warp_cnt = s_meta + tpb;
+  unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_warp_cnt + 32);
 
   const int tid = threadIdx.x;
   const int N = a.N;
@@ -350,27 +456,38 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   const bool valid = (le < a.envs_per_block) && (env < a.E);
   const int g = env * N + la;
 
-  float2 p = v2(0.f, 0.f), v = v2(0.f, 0.f);
+  AgentCarry c;
+  c.p = v2(0.f, 0.f);
+  c.v = v2(0.f, 0.f);
+  c.nv = v2(0.f, 0.f);
+  c.n = c.n_obst = c.fail = 0;
   int estep = 0;
   if (valid) {
-    p = a.pos[g];
-    v = a.vel[g];
-    s_pos[tid] = p;
-    s_vel[tid] = v;
+    c.p = a.pos[g];
+    c.v = a.vel[g];
+    s_pos[tid] = c.p;
+    s_vel[tid] = c.v;
     if (a.env_step != nullptr) estep = a.env_step[env];
   }
   __syncthreads();
   const unsigned warp_mask = __ballot_sync(0xffffffffu, valid);  // lanes that run the step
-  if (!valid) return;
-  Lines L;
-  L.base = s_lines + tid;
-  L.stride = tpb;
-  TileSource src;
-  src.env_pos = s_pos + le * N;
-  src.env_vel = s_vel + le * N;
-  src.n = N;
-  src.self = la;
-  agent_step_body<K, KFULL, POLICY>(a, env, la, g, p, v, estep, src, L, warp_mask);
+  bool alive = valid;
+  if (valid) {
+    Lines L;
+    L.base = s_lines + tid;
+    L.stride = tpb;
+    TileSource src;
+    src.env_pos = s_pos + le * N;
+    src.env_vel = s_vel + le * N;
+    src.n = N;
+    src.self = la;
+    alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, L, warp_mask, c);
+  }
+  if (a.neighbors_only) return;  // uniform over the grid
+  block_lp3<K>(s_lines, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);
+  if (!alive) return;
+  c.nv = s_nv[tid];
+  agent_back<POLICY>(a, env, la, g, estep, c);
 }
 
 #endif  // __CUDACC__

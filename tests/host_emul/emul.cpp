@@ -61,7 +61,7 @@ void run_grid_k(const orca::StepArgs& a0, int policy) {
     mxx = std::fmax(mxx, a.pos[i].x); mxy = std::fmax(mxy, a.pos[i].y);
   }
   orca::GridParams gp;
-  const float cell = std::sqrt(a.nd_sq);
+  const float cell = orca::grid_cell_size(std::sqrt(a.nd_sq));
   gp.origin_x = mnx; gp.origin_y = mny; gp.inv_cell = 1.0f / cell;
   gp.W = (int)(std::floor((mxx - mnx) / cell) + 1.f);
   gp.H = (int)(std::floor((mxy - mny) / cell) + 1.f);
