@@ -99,23 +99,41 @@ struct GridSource {
   }
 
   template <class NK>
-  ORCA_HD void gather(NK& nk, float2 p) const {
+  ORCA_HD void gather(NK& nk, float2 p, const Lines& scratch, int scratch_slots, unsigned mask) const {
     const int cx = cell_coord(p.x, gp.origin_x, gp.inv_cell, gp.W);
     const int cy = cell_coord(p.y, gp.origin_y, gp.inv_cell, gp.H);
     const int base = env * gp.W * gp.H;
     Before before;
     before.orig = orig;
+    CandidateBuffer buf;
+    buf.base = scratch.base;
+    buf.stride = scratch.stride;
+    buf.cap = scratch_slots;
+    buf.cnt = 0;
+    auto insert = [&nk, &before](float d, int id) { nk.offer_ranked(d, id, before); };
     const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < gp.W ? cx + 1 : gp.W - 1;
-    for (int yy = (cy > 0 ? cy - 1 : 0); yy <= (cy + 1 < gp.H ? cy + 1 : gp.H - 1); ++yy) {
-      // the cells (x0..x1, yy) are consecutive keys: one contiguous range of the sorted arrays
-      const int first = ORCA_LDG(&cell_start[base + yy * gp.W + x0]);
-      const int last = ORCA_LDG(&cell_start[base + yy * gp.W + x1 + 1]);
-      for (int q = first; q < last; ++q) {
-        if (q == self) continue;
-        const float2 o = ORCA_LDG(&spos[q]);
-        nk.offer_ranked(abs_sq(sub(p, o)), q, before);
+    // three rows of cells; the cells (x0..x1, row) are consecutive keys, i.e. one contiguous range
+    // of the sorted arrays.  Lanes walk their own ranges but vote together on every iteration.
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = cy + dy;
+      int q = 0, last = 0;
+      if (yy >= 0 && yy < gp.H) {
+        q = ORCA_LDG(&cell_start[base + yy * gp.W + x0]);
+        last = ORCA_LDG(&cell_start[base + yy * gp.W + x1 + 1]);
+      }
+      while (ORCA_ANY(mask, q < last)) {
+        if (q < last) {
+          if (q != self) {
+            const float2 o = ORCA_LDG(&spos[q]);
+            const float d = abs_sq(sub(p, o));
+            if (d <= nk.thresh()) buf.push(d, q);
+          }
+          ++q;
+        }
+        buf.drain_if_full(mask, insert);
       }
     }
+    buf.drain(mask, insert);
   }
   ORCA_HD float2 pos(int q) const { return ORCA_LDG(&spos[q]); }
   ORCA_HD float2 vel(int q) const { return ORCA_LDG(&svel[q]); }
@@ -310,7 +328,8 @@ __global__ void __launch_bounds__(128, 6) step_grid_kernel(const StepArgs a, con
   extern __shared__ float4 smem4[];
   const int tpb = blockDim.x;
   float4* s_lines = smem4;
-  float2* s_nv = reinterpret_cast<float2*>(s_lines + (K + ORCA_MAX_OBST_LINES) * tpb);
+  float4* s_pool = s_lines + (K + ORCA_MAX_OBST_LINES) * tpb;
+  float2* s_nv = reinterpret_cast<float2*>(s_pool + (ORCA_LP3_SMEM_POOL ? (K + ORCA_MAX_OBST_LINES) * (tpb / 2) : 0));
   int* s_meta = reinterpret_cast<int*>(s_nv + tpb);
   int* s_warp_cnt = s_meta + tpb;
   unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_warp_cnt + 32);
@@ -347,7 +366,7 @@ __global__ void __launch_bounds__(128, 6) step_grid_kernel(const StepArgs a, con
     alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
-  block_lp3<K>(s_lines, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);
+  block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);
   if (!alive) return;
   c.nv = s_nv[threadIdx.x];
   agent_back<POLICY>(a, env, la, g, estep, c);

@@ -106,12 +106,31 @@ struct TileSource {
   int n;
   int self;
   template <class NK>
-  ORCA_HD void gather(NK& nk, float2 p) const {
-    for (int j = 0; j < n; ++j) {
-      if (j == self) continue;
-      const float2 q = env_pos[j];
-      nk.offer(abs_sq(sub(p, q)), j);
+  ORCA_HD void gather(NK& nk, float2 p, const Lines& scratch, int scratch_slots, unsigned mask) const {
+    if (n <= 32) {
+      // few candidates, most of them accepted by most lanes: insert directly
+      for (int j = 0; j < n; ++j) {
+        if (j == self) continue;
+        const float2 q = env_pos[j];
+        nk.offer(abs_sq(sub(p, q)), j);
+      }
+      return;
     }
+    CandidateBuffer buf;
+    buf.base = scratch.base;
+    buf.stride = scratch.stride;
+    buf.cap = scratch_slots;
+    buf.cnt = 0;
+    auto insert = [&nk](float d, int id) { nk.offer(d, id); };
+    for (int j = 0; j < n; ++j) {  // n is uniform over the warp's envs
+      if (j != self) {
+        const float2 q = env_pos[j];
+        const float d = abs_sq(sub(p, q));
+        if (d < nk.thresh()) buf.push(d, j);
+      }
+      buf.drain_if_full(mask, insert);
+    }
+    buf.drain(mask, insert);
   }
   ORCA_HD float2 pos(int q) const { return env_pos[q]; }
   ORCA_HD float2 vel(int q) const { return env_vel[q]; }
@@ -236,7 +255,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
 
   NearestK<K, KFULL> nk;
   nk.init(a.k, a.nd_sq);
-  src.gather(nk, p);
+  src.gather(nk, p, L, K + ORCA_MAX_OBST_LINES, warp_mask);
 
   if (a.nbr_idx != nullptr) {
     int cnt = 0;
@@ -370,9 +389,16 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
 #define ORCA_STEP_MIN_BLOCKS 3
 #endif
 
+#ifndef ORCA_LP3_SMEM_POOL
+#define ORCA_LP3_SMEM_POOL 0
+#endif
 // dynamic shared memory of the step kernels: [pos|vel tile (tile path only)] + lines + LP3 queue
 inline size_t step_smem_bytes(int K, int tpb, bool tile) {
-  return (size_t)tpb * ((tile ? 16 : 0) + (size_t)(K + ORCA_MAX_OBST_LINES) * 16 + 8 + 4 + 2) + 32 * 4;
+  size_t b = (size_t)tpb * ((tile ? 16 : 0) + (size_t)(K + ORCA_MAX_OBST_LINES) * 16 + 8 + 4 + 2) + 32 * 4;
+#if ORCA_LP3_SMEM_POOL
+  b += (size_t)(tpb / 2) * (K + ORCA_MAX_OBST_LINES) * 16 + 16;  // LP3 projected-line pool
+#endif
+  return b;
 }
 
 // LP3 with block-level work compaction.  Only the agents whose LP2 was infeasible need LP3
@@ -385,9 +411,12 @@ inline size_t step_smem_bytes(int K, int tpb, bool tile) {
 #ifndef ORCA_BLOCK_LP3
 #define ORCA_BLOCK_LP3 1
 #endif
+#ifndef ORCA_LP3_SMEM_POOL
+#define ORCA_LP3_SMEM_POOL 0
+#endif
 template <int K>
-__device__ __forceinline__ void block_lp3(float4* s_lines, int* s_meta, float2* s_nv, unsigned short* s_queue,
-                                          int* s_warp_cnt, const bool need, const AgentCarry& c, const float vmax) {
+__device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* s_meta, float2* s_nv,
+                                          unsigned short* s_queue, int* s_warp_cnt, const bool need, const AgentCarry& c, const float vmax) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 #if !ORCA_BLOCK_LP3
   {  // in-place variant (kept for A/B measurements): every thread solves its own agent
@@ -417,6 +446,29 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, int* s_meta, float2* 
   }
   if (need) s_queue[offset + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)tid;
   __syncthreads();
+#if ORCA_LP3_SMEM_POOL
+  // projected lines in a shared-memory pool of blockDim/2 entries (SoA, stride = pool size);
+  // the queue is drained in passes of that many agents by the first half of the block
+  const int pool = blockDim.x >> 1;
+  for (int first = 0; first < total; first += pool) {
+    if ((warp << 5) < pool && first + (warp << 5) < total) {  // warp-uniform
+      const int slot = first + tid;
+      const bool mine = slot < total;
+      const int owner = mine ? (int)s_queue[slot] : tid;
+      const int meta = s_meta[owner];
+      Lines L;
+      L.base = s_lines + owner;
+      L.stride = blockDim.x;
+      Lines P;
+      P.base = s_pool + tid;
+      P.stride = pool;
+      float2 nv = s_nv[owner];
+      lp3(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, P, nv);
+      if (mine) s_nv[owner] = nv;
+    }
+  }
+#else
+  (void)s_pool;
   if ((warp << 5) < total) {  // warp-uniform: this warp owns queue entries
     const bool mine = tid < total;
     const int owner = mine ? (int)s_queue[tid] : tid;
@@ -431,6 +483,7 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, int* s_meta, float2* 
     lp3(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, P, nv);
     if (mine) s_nv[owner] = nv;
   }
+#endif
   __syncthreads();
 }
 
@@ -443,7 +496,8 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   float2* s_pos = reinterpret_cast<float2*>(smem4);
   float2* s_vel = s_pos + tpb;
   float4* s_lines = smem4 + tpb;
-  float2* s_nv = reinterpret_cast<float2*>(s_lines + (K + ORCA_MAX_OBST_LINES) * tpb);
+  float4* s_pool = s_lines + (K + ORCA_MAX_OBST_LINES) * tpb;
+  float2* s_nv = reinterpret_cast<float2*>(s_pool + (ORCA_LP3_SMEM_POOL ? (K + ORCA_MAX_OBST_LINES) * (tpb / 2) : 0));
   int* s_meta = reinterpret_cast<int*>(s_nv + tpb);
   int* s_warp_cnt = s_meta + tpb;
   unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_warp_cnt + 32);
@@ -484,7 +538,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
     alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
-  block_lp3<K>(s_lines, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);
+  block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);
   if (!alive) return;
   c.nv = s_nv[tid];
   agent_back<POLICY>(a, env, la, g, estep, c);
