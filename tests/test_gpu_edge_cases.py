@@ -1,0 +1,136 @@
+"""GPU edge cases of the C-ABI path: ragged batch shapes, degenerate parameters, the env
+policies on the uniform-grid path, error surfacing."""
+import numpy as np
+import pytest
+
+from _common import goal_pref, oracle_sims
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(scn, **env):
+    import torch
+    from collision_avoidance_b200.sim import BatchedRVOSimulator
+    sim = BatchedRVOSimulator(scn.num_envs, scn.agents_per_env, device="cuda:0", **scn.params)
+    sim.set_obstacles(scn.obstacles, per_env=scn.per_env_obstacles)
+    sim.pos.copy_(torch.from_numpy(scn.pos))
+    sim.vel.copy_(torch.from_numpy(scn.vel))
+    return sim
+
+
+def _one_step_vs_oracle(scn, steps=20):
+    import torch
+    gpu = _mk(scn)
+    sims = oracle_sims(scn)
+    for _ in range(steps):
+        pos = np.stack([s.positions() for s in sims])
+        vel = np.stack([s.velocities() for s in sims])
+        pref = goal_pref(pos, scn.goal).astype(np.float32)
+        for e, s in enumerate(sims):
+            s.set_pref_velocities(pref[e])
+            s.doStep()
+        gpu.pos.copy_(torch.from_numpy(pos))
+        gpu.vel.copy_(torch.from_numpy(vel))
+        gpu.pref.copy_(torch.from_numpy(pref))
+        gpu.doStep()
+        assert np.abs(gpu.vel.cpu().numpy() - np.stack([s.velocities() for s in sims])).max() <= 1e-4
+        assert np.abs(gpu.pos.cpu().numpy() - np.stack([s.positions() for s in sims])).max() <= 1e-4
+
+
+@pytest.mark.parametrize("E,N", [(1, 1), (3, 7), (5, 10), (37, 16), (2, 100), (3, 129), (1, 256), (2, 257), (1, 1000)])
+def test_ragged_shapes_match_oracle(E, N):
+    from collision_avoidance_b200 import scenarios
+    _one_step_vs_oracle(scenarios.crowd(E, N, seed=E * 1000 + N), steps=8)
+
+
+@pytest.mark.parametrize("k,nd", [(0, 5.0), (1, 5.0), (3, 2.0), (7, 5.0), (13, 3.0), (16, 8.0)])
+def test_generic_max_neighbors(k, nd):
+    from collision_avoidance_b200 import scenarios
+    scn = scenarios.crowd(3, 40, seed=k + 50)
+    scn.params = dict(scn.params, maxNeighbors=k, neighborDist=nd)
+    _one_step_vs_oracle(scn, steps=10)
+
+
+def test_no_obstacles_and_per_env_obstacles():
+    from collision_avoidance_b200 import scenarios
+    scn = scenarios.crowd(4, 30, seed=60)
+    scn.obstacles = []
+    _one_step_vs_oracle(scn, steps=10)
+    _one_step_vs_oracle(scenarios.blocks(5, 14, seed=61), steps=15)
+
+
+def test_env_policies_on_grid_path_equal_tile_path(monkeypatch):
+    """ALAN bandit + done test, and the RL policy, stepped through the uniform-grid pipeline
+    give the same bits as the shared-memory tile path (env counters bumped by the side kernel)."""
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    from collision_avoidance_b200.alan import DEFAULT_ONLINE_ACTIONS, unit_actions
+    scn = scenarios.circle(6, 48, seed=70)
+    E, N = 6, 48
+    dev = "cuda:0"
+    acts = torch.from_numpy(unit_actions(DEFAULT_ONLINE_ACTIONS)).to(dev)
+    sims = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("ORCA_B200_GRID_MIN_AGENTS", "2")
+        sims.append(_mk(scn))
+    monkeypatch.delenv("ORCA_B200_GRID_MIN_AGENTS")
+
+    def fresh():
+        return dict(goal=torch.from_numpy(scn.goal).to(dev), goal2=torch.from_numpy(scn.goal2).to(dev),
+                    agent_done=torch.zeros(E, N, dtype=torch.uint8, device=dev),
+                    arrival_time=torch.zeros(E, N, device=dev), env_step=torch.zeros(E, dtype=torch.int32, device=dev),
+                    env_done_cnt=torch.zeros(E, dtype=torch.int32, device=dev), reward=torch.zeros(E, N, device=dev))
+    st = [fresh(), fresh()]
+    w = [torch.zeros(E, N, 8, device=dev), torch.zeros(E, N, 8, device=dev)]
+    ids = [torch.zeros(E, N, dtype=torch.uint8, device=dev), torch.zeros(E, N, dtype=torch.uint8, device=dev)]
+    for t in range(130):  # crosses the 121-step weight reset
+        for s, state, ww, ii in zip(sims, st, w, ids):
+            s.env_step(policy=_lib.POLICY_ALAN, done_mode=_lib.DONE_GOAL_RADIUS, alan_weights=ww, alan_actions=acts,
+                       alan_action_out=ii, rng_seed=99, **state)
+    assert torch.equal(sims[0].pos, sims[1].pos) and torch.equal(w[0], w[1]) and torch.equal(ids[0], ids[1])
+    assert torch.equal(st[0]["env_step"], st[1]["env_step"]) and int(st[0]["env_step"][0]) == 130
+    assert torch.equal(st[0]["reward"], st[1]["reward"])
+    theta = (torch.rand(E, N, device=dev) - 0.5) * 2.0
+    for s, state in zip(sims, st):
+        s.env_step(policy=_lib.POLICY_RL, done_mode=_lib.DONE_X_BELOW, action_theta=theta, goal=state["goal"],
+                   goal2=state["goal2"], agent_done=state["agent_done"], env_step=state["env_step"],
+                   env_done_cnt=state["env_done_cnt"], reward=state["reward"])
+    assert torch.equal(sims[0].vel, sims[1].vel) and torch.equal(st[0]["reward"], st[1]["reward"])
+
+
+def test_errors_surface_as_python_exceptions():
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    from collision_avoidance_b200.sim import BatchedRVOSimulator
+    with pytest.raises(NotImplementedError):
+        BatchedRVOSimulator(2, 8, 1 / 60., 5.0, 17, 1.5, 1.5, 0.5, 1.0)       # maxNeighbors > 16
+    with pytest.raises(ValueError):
+        BatchedRVOSimulator(2, 8, 1 / 60., 5.0, 10, 1.5, 1.5, 0.5, 1.0, device="cpu")   # no CPU path
+    sim = BatchedRVOSimulator(2, 8, 1 / 60., 5.0, 10, 1.5, 1.5, 0.5, 1.0)
+    with pytest.raises(ValueError):
+        sim.env_step(policy=_lib.POLICY_GOAL)                                   # goal missing
+    with pytest.raises(ValueError):
+        sim.env_step(policy=_lib.POLICY_GOAL, goal=torch.zeros(2, 8, 2))        # CPU tensor
+    with pytest.raises(ValueError):
+        sim.set_obstacles([[(0.0, 0.0)]])                                        # 1-vertex polygon
+    with pytest.raises(ValueError):
+        sim.env_step(policy=_lib.POLICY_GOAL, goal=torch.zeros(2, 8, 2, device="cuda"), done_mode=_lib.DONE_GOAL_RADIUS)
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    scn = scenarios.circle(64, 16, seed=80)
+    a, b = _mk(scn), _mk(scn)
+    goal = torch.from_numpy(scn.goal).cuda()
+    pos_h = torch.from_numpy(scn.pos.copy()).pin_memory()
+    vel_h = torch.from_numpy(scn.vel.copy()).pin_memory()
+    goal_h = torch.from_numpy(scn.goal.copy()).pin_memory()
+    b.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=1)
+    a.env_step(policy=_lib.POLICY_GOAL, goal=goal)
+    for _ in range(20):
+        a.env_step(policy=_lib.POLICY_GOAL, goal=goal)
+        b.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
+    assert np.array_equal(a.pos.cpu().numpy(), pos_h.numpy().reshape(64, 16, 2))
+    assert np.array_equal(a.vel.cpu().numpy(), vel_h.numpy().reshape(64, 16, 2))
