@@ -79,6 +79,9 @@ class OrcaEnvStepArgs(ctypes.Structure):
         ("alan_gamma", ctypes.c_float),
         ("alan_temp", ctypes.c_float),
         ("rng_seed", ctypes.c_uint64),
+        ("alan_num_actions_env_dev", _vp),
+        ("alan_actions_env_stride", ctypes.c_int32),
+        ("_pad1", ctypes.c_int32),
         ("reward_dev", _vp),
         ("agent_done_dev", _vp),
         ("arrival_time_dev", _vp),

@@ -106,11 +106,27 @@ class Collision_Avoidance_Sim:
         self.TTime = torch.zeros(E, dtype=torch.float64, device=dev)
 
     def _set_actions(self, actions):
-        self.online_actions = list(actions)
-        A = len(self.online_actions)
-        if not 1 <= A <= _lib.MAX_ACTIONS:
-            raise ValueError(f"between 1 and {_lib.MAX_ACTIONS} online actions are supported, got {A}")
-        self.action_table = torch.from_numpy(unit_actions(self.online_actions)).to(self.device)
+        """``actions``: one action set for every world (the reference's form), or a list of
+        ``num_envs`` action sets -- one per world -- for batched action-space search."""
+        per_env = len(actions) > 0 and isinstance(actions[0], (list, tuple)) and len(actions[0]) > 0 and \
+            isinstance(actions[0][0], (list, tuple))
+        self.online_actions = [list(a) for a in actions] if per_env else list(actions)
+        sets = self.online_actions if per_env else [self.online_actions]
+        if per_env and len(sets) != self.num_envs:
+            raise ValueError("per-world action sets need one set per world")
+        A = max(len(a) for a in sets)
+        if min(len(a) for a in sets) < 1 or A > _lib.MAX_ACTIONS:
+            raise ValueError(f"between 1 and {_lib.MAX_ACTIONS} online actions are supported")
+        if per_env:
+            table = np.zeros((self.num_envs, A, 2), np.float32)
+            table[..., 0] = 1.0
+            for e, a in enumerate(sets):
+                table[e, :len(a)] = unit_actions(a)
+            self.action_table = torch.from_numpy(table).to(self.device)
+            self.action_counts = torch.tensor([len(a) for a in sets], dtype=torch.int32, device=self.device)
+        else:
+            self.action_table = torch.from_numpy(unit_actions(self.online_actions)).to(self.device)
+            self.action_counts = None
         self.action_weights = torch.zeros(self.num_envs, self.numAgents, A, dtype=torch.float32, device=self.device)
         self.window_steps = alan_window_steps(self.timeStep, self.timewindow)
 
@@ -127,6 +143,7 @@ class Collision_Avoidance_Sim:
         self.sim.env_step(policy=_lib.POLICY_ALAN, goal=self.goal, goal2=self.goal2, done_mode=_lib.DONE_GOAL_RADIUS,
                           alan_weights=self.action_weights, alan_actions=self.action_table,
                           alan_action_out=self.action_ids, alan_uniform=uniforms,
+                          alan_num_actions_env=self.action_counts,
                           alan_window_steps=self.window_steps, alan_gamma=self.gamma, alan_temp=self.online_temp,
                           rng_seed=self.seed * 1_000_003 + self._episode, reward=self.reward,
                           agent_done=self.agents_done, arrival_time=self.agents_time, env_step=self.env_step,

@@ -366,6 +366,8 @@ int orca_env_step(OrcaSim* s, const OrcaEnvStepArgs* in, void* stream) {
     if (in->alan_num_actions < 1 || in->alan_num_actions > ORCA_MAX_ACTIONS)
       return fail(ORCA_ERR_UNSUPPORTED, "alan_num_actions must be in [1, %d]", ORCA_MAX_ACTIONS);
     if (!(in->alan_temp > 0.f)) return fail(ORCA_ERR_INVALID, "alan_temp must be > 0");
+    if (in->alan_actions_env_stride < 0 || (in->alan_actions_env_stride > 0 && in->alan_actions_env_stride < in->alan_num_actions))
+      return fail(ORCA_ERR_INVALID, "alan_actions_env_stride must be 0 or >= alan_num_actions");
   }
   if (in->done_mode != ORCA_DONE_NONE) {
     if (in->agent_done_dev == nullptr) return fail(ORCA_ERR_INVALID, "done_mode needs agent_done_dev");
@@ -394,6 +396,8 @@ int orca_env_step(OrcaSim* s, const OrcaEnvStepArgs* in, void* stream) {
   a.alan_gamma = in->alan_gamma;
   a.alan_inv_temp = (in->policy == ORCA_POLICY_ALAN) ? 1.0f / in->alan_temp : 0.f;
   a.seed = in->rng_seed;
+  a.alan_A_env = in->alan_num_actions_env_dev;
+  a.alan_env_stride = in->alan_actions_env_stride;
   a.reward = in->reward_dev;
   a.done = in->agent_done_dev;
   a.arrival = in->arrival_time_dev;

@@ -57,6 +57,8 @@ struct StepArgs {
   int A, alan_window;
   float alan_gamma, alan_inv_temp;
   unsigned long long seed;
+  const int* alan_A_env;  // per-env action count (NULL: A everywhere)
+  int alan_env_stride;    // per-env action table stride in float2 (0: shared table)
   // outputs
   float* reward;
   uint8_t* done;
@@ -204,10 +206,12 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
     if (POLICY == POLICY_ALAN) {
       // softmax over the last rewards; inverse-CDF draw like np.random.choice(p=ps)
       const float* wrow = a.alan_w + (size_t)g * a.A;
+      const int nA = (a.alan_A_env != nullptr) ? a.alan_A_env[env] : a.A;  // this env's action count
+      const float2* table = a.alan_actions + (size_t)env * a.alan_env_stride;
       float total = 0.f;
 #pragma unroll
       for (int i = 0; i < ORCA_MAX_ACTIONS; ++i) {
-        if (i < a.A) {
+        if (i < nA) {
           w_act[i] = expf(wrow[i] * a.alan_inv_temp);
           total += w_act[i];
         }
@@ -217,11 +221,11 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
                           : philox_uniform(a.seed, (uint32_t)g, (uint32_t)estep);
       const float target = u * total;
       float run = 0.f;
-      act = a.A - 1;
+      act = nA - 1;
       bool found = false;
 #pragma unroll
       for (int i = 0; i < ORCA_MAX_ACTIONS; ++i) {
-        if (i < a.A) {
+        if (i < nA) {
           run += w_act[i];
           if (!found && run > target) {
             act = i;
@@ -229,7 +233,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
           }
         }
       }
-      pref = rotate(gdir, a.alan_actions[act]);
+      pref = rotate(gdir, table[act]);
       if (a.alan_action_out != nullptr) a.alan_action_out[g] = (uint8_t)act;
     }
   }

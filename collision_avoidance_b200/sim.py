@@ -184,6 +184,7 @@ class BatchedRVOSimulator:
                  rl_reward_scale: float = 0.3, done_x_threshold: float = 2.0,
                  alan_weights: Optional[torch.Tensor] = None, alan_actions: Optional[torch.Tensor] = None,
                  alan_action_out: Optional[torch.Tensor] = None, alan_uniform: Optional[torch.Tensor] = None,
+                 alan_num_actions_env: Optional[torch.Tensor] = None,
                  alan_window_steps: int = 121, alan_gamma: float = 0.6, alan_temp: float = 0.2, rng_seed: int = 0,
                  reward: Optional[torch.Tensor] = None, agent_done: Optional[torch.Tensor] = None,
                  arrival_time: Optional[torch.Tensor] = None, env_step: Optional[torch.Tensor] = None,
@@ -208,9 +209,17 @@ class BatchedRVOSimulator:
             a.action_theta_dev = action_theta.data_ptr()
         a.rl_reward_scale, a.done_x_threshold = float(rl_reward_scale), float(done_x_threshold)
         if alan_weights is not None:
-            A = alan_actions.shape[0]
+            # alan_actions: [A, 2] shared by all envs, or [E, A, 2] one table per env
+            A = alan_actions.shape[-2]
             self._check_state(alan_weights, (E, N, A), torch.float32, "alan_weights")
-            self._check_state(alan_actions, (A, 2), torch.float32, "alan_actions")
+            if alan_actions.dim() == 3:
+                self._check_state(alan_actions, (E, A, 2), torch.float32, "alan_actions")
+                a.alan_actions_env_stride = A
+                if alan_num_actions_env is not None:
+                    self._check_state(alan_num_actions_env, (E,), torch.int32, "alan_num_actions_env")
+                    a.alan_num_actions_env_dev = alan_num_actions_env.data_ptr()
+            else:
+                self._check_state(alan_actions, (A, 2), torch.float32, "alan_actions")
             a.alan_weights_dev, a.alan_actions_dev, a.alan_num_actions = alan_weights.data_ptr(), alan_actions.data_ptr(), A
             if alan_action_out is not None:
                 self._check_state(alan_action_out, (E, N), torch.uint8, "alan_action_out")

@@ -107,11 +107,17 @@ typedef struct OrcaEnvStepArgs {
   const float* alan_actions_dev;    /* [A][2]  unit vectors: online_actions (ALAN :31-38, *.act files) */
   uint8_t* alan_action_out_dev;     /* [E*N] chosen action id, optional */
   const float* alan_uniform_in_dev; /* [E*N] optional: externally supplied U[0,1) draws (parity tests) */
-  int32_t alan_num_actions;         /* A <= 16 */
+  int32_t alan_num_actions;         /* A <= 16 (row length of alan_weights_dev; max over envs) */
   int32_t alan_window_steps;        /* steps between global weight resets: 121 for dt=1/60, window 2 s */
   float alan_gamma;                 /* 0.6 (ALAN :47) */
   float alan_temp;                  /* 0.2 (ALAN :49) */
   uint64_t rng_seed;                /* Philox key; counter = (global agent id, env step) */
+  /* per-env action sets (batched action-space search, Train_ALAN_action_space.py:55-67): when
+   * alan_actions_env_stride > 0, env e reads its table at alan_actions_dev + e*stride*2 floats and
+   * uses alan_num_actions_env_dev[e] (<= alan_num_actions) of its entries */
+  const int32_t* alan_num_actions_env_dev; /* [E] or NULL */
+  int32_t alan_actions_env_stride;         /* actions per env slot, 0 = one shared table */
+  int32_t _pad1;
 
   /* per-step outputs */
   float* reward_dev;         /* [E*N] optional */

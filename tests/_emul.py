@@ -26,7 +26,7 @@ class StepArgs(ctypes.Structure):
         ("action_theta", c_p), ("rl_scale", c_f), ("done_x", c_f),
         ("alan_w", c_p), ("alan_actions", c_p), ("alan_action_out", c_p), ("alan_uniform_in", c_p),
         ("A", c_i), ("alan_window", c_i), ("alan_gamma", c_f), ("alan_inv_temp", c_f),
-        ("seed", ctypes.c_ulonglong),
+        ("seed", ctypes.c_ulonglong), ("alan_A_env", c_p), ("alan_env_stride", c_i),
         ("reward", c_p), ("done", c_p), ("arrival", c_p), ("env_step", c_p), ("env_done_cnt", c_p),
         ("done_mode", c_i),
         ("nbr_idx", c_p), ("nbr_dsq", c_p), ("nbr_cnt", c_p), ("onbr_idx", c_p), ("onbr_cnt", c_p),

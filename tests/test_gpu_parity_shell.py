@@ -220,3 +220,43 @@ def test_compat_shim_runs_the_shell_logic_like_the_oracle():
     assert c.action_weights == d.action_weights
     for i in range(12):
         assert c.sim.getAgentPosition(i) == d.sim.getAgentPosition(i)
+
+
+def test_per_world_action_tables_match_separate_runs():
+    """Row f1: worlds with their own action sets (different sizes) in one batch behave exactly
+    like separate single-table runs of the same worlds under the same draws."""
+    torch = _torch()
+    import json
+    import os
+    from collision_avoidance_b200 import alan
+    with open(os.path.join(os.path.dirname(__file__), "golden", "act_tables.json")) as f:
+        tabs = json.load(f)
+    sets = [[tuple(a) for a in tabs["circle"]], [tuple(a) for a in tabs["crowd"]], list(alan.DEFAULT_ONLINE_ACTIONS)]
+    N, steps = 12, 150
+    batch = alan.Collision_Avoidance_Sim(numAgents=N, scenario="circle", online_actions=sets, num_envs=3, seed=31)
+    singles = []
+    for e in range(3):
+        s = alan.Collision_Avoidance_Sim(numAgents=N, scenario="circle", online_actions=sets[e], num_envs=3, seed=31)
+        singles.append(s)
+    rng = np.random.default_rng(1)
+    for t in range(steps):
+        u = torch.from_numpy(rng.random((3, N)).astype(np.float32)).cuda()
+        batch.online_step(uniforms=u)
+        for s in singles:
+            s.online_step(uniforms=u)
+    for e in range(3):
+        assert torch.equal(batch.sim.pos[e], singles[e].sim.pos[e])
+        A = len(sets[e])
+        assert torch.equal(batch.action_weights[e, :, :A], singles[e].action_weights[e])
+        assert int(batch.action_ids[e].max()) < A
+
+
+def test_mcmc_trainer_runs_and_never_worsens_the_best():
+    from collision_avoidance_b200 import mcmc
+    tr = mcmc.MCMC_trainer(numAgents=8, scenario="circle", numRounds=4, chains=4, sims_per_eval=3, seed=5, max_steps=1500)
+    first = min(tr.eval_opt)
+    best = tr.train()
+    assert best[0] == (1, 0) and 1 <= len(best) <= 16
+    assert min(tr.eval_opt) <= first
+    assert all(abs(a[0] ** 2 + a[1] ** 2 - 1) < 1e-9 for a in best)
+    assert tr.temp < 0.9     # annealing cools down (the reference heats up; see module docstring)
