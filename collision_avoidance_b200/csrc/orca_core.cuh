@@ -110,6 +110,11 @@ struct Lines {
   float4* base;
   int stride;
   ORCA_HD float4 get(int i) const { return base[i * stride]; }
+  // line-source protocol of the LPs: fetch(j, out) -> false when virtual line j does not exist
+  ORCA_HD bool fetch(int i, float4& out) const {
+    out = base[i * stride];
+    return true;
+  }
   ORCA_HD void set(int i, float2 point, float2 dir) const {
     float4 v;
     v.x = point.x;
@@ -143,10 +148,13 @@ struct ObstacleWorld {
 #endif
 
 // ---- linear programs -------------------------------------------------------------
-// LP1: optimise along line i subject to the speed disc and lines [0, i).
+// The LPs read their constraints through a "line source" S: S.fetch(j, out) yields virtual line j
+// or reports that it does not exist.  `Lines` (the agent's ORCA lines in shared memory) always
+// has every line; `ProjectedLines` below is LP3's projected programme, computed on the fly.
+
+// LP1: optimise along line i (= li, already fetched) subject to the speed disc and lines [0, i).
 template <class LS>
-ORCA_HD bool lp1(const LS& L, int i, float radius, float2 opt, bool dir_opt, float2& result) {
-  const float4 li = L.get(i);
+ORCA_HD bool lp1(const LS& S, int i, float4 li, float radius, float2 opt, bool dir_opt, float2& result) {
   const float2 pi = pt(li), di = dr(li);
   const float dp = dot(pi, di);
   const float disc = sqr(dp) + sqr(radius) - abs_sq(pi);
@@ -157,7 +165,8 @@ ORCA_HD bool lp1(const LS& L, int i, float radius, float2 opt, bool dir_opt, flo
   ORCA_COUNT(2, 1);  // lp1 calls
   ORCA_COUNT(3, i);  // lp1 inner iterations (upper bound)
   for (int j = 0; j < i; ++j) {
-    const float4 lj = L.get(j);
+    float4 lj;
+    if (!S.fetch(j, lj)) continue;
     const float den = det(di, dr(lj));
     const float num = det(dr(lj), sub(pi, pt(lj)));
     if (fabsf(den) <= kEps) {
@@ -200,9 +209,10 @@ ORCA_HD bool lp1(const LS& L, int i, float radius, float2 opt, bool dir_opt, flo
 #define ORCA_CONVERGE(mask) ((void)0)
 #endif
 
-// LP2: returns the index of the first line that cannot be satisfied (n on success).
+// LP2 over the virtual lines [0, n) of S: returns the index of the first line that cannot be
+// satisfied (n on success).
 template <class LS>
-ORCA_HD int lp2(unsigned mask, bool enabled, const LS& L, int n, float radius, float2 opt, bool dir_opt,
+ORCA_HD int lp2(unsigned mask, bool enabled, const LS& S, int n, float radius, float2 opt, bool dir_opt,
                 float2& result) {
   if (dir_opt) {
     result = mul(radius, opt);  // opt * radius
@@ -215,10 +225,11 @@ ORCA_HD int lp2(unsigned mask, bool enabled, const LS& L, int n, float radius, f
   int fail = n;
   bool active = enabled;
   while (ORCA_ANY(mask, active)) {
+    float4 li;
+    li.x = li.y = li.z = li.w = 0.f;
     if (active) {
       while (i < n) {
-        const float4 li = L.get(i);
-        if (det(dr(li), sub(pt(li), result)) > 0.f) break;
+        if (S.fetch(i, li) && det(dr(li), sub(pt(li), result)) > 0.f) break;
         ++i;
       }
       active = i < n;
@@ -226,7 +237,7 @@ ORCA_HD int lp2(unsigned mask, bool enabled, const LS& L, int n, float radius, f
     ORCA_CONVERGE(mask);
     if (active) {
       const float2 keep = result;
-      if (!lp1(L, i, radius, opt, dir_opt, result)) {
+      if (!lp1(S, i, li, radius, opt, dir_opt, result)) {
         result = keep;
         fail = i;
         active = false;
@@ -237,12 +248,85 @@ ORCA_HD int lp2(unsigned mask, bool enabled, const LS& L, int n, float radius, f
   return fail;
 }
 
+// LP3's projected programme for ORCA line i, as a line source computed on the fly: virtual
+// line j is obstacle line j as it is (j < n_obst, kept hard), or agent line j (n_obst <= j < i)
+// projected onto line i; lines parallel to line i in the same direction do not exist
+// (RVO2 `continue`s over them).  Recomputing a projection costs ~45 FP32 instructions from two
+// shared-memory lines; storing the programme instead needed a per-thread local-memory array
+// whose load/store latency made LP3 41 % of the whole step.
+template <class LS>
+struct ProjectedLines {
+  LS L;
+  float2 pi, di;  // line i
+  int n_obst;
+  ORCA_HD bool fetch(int j, float4& out) const {
+    ORCA_COUNT(4, 1);  // projected-line fetches
+    const float4 lj = L.get(j);
+    if (j < n_obst) {
+      out = lj;
+      return true;
+    }
+    const float2 pj = pt(lj), dj = dr(lj);
+    const float d = det(di, dj);
+    float2 np;
+    if (fabsf(d) <= kEps) {
+      if (dot(di, dj) > 0.f) return false;
+      np = mul(0.5f, add(pi, pj));
+    } else {
+      np = add(pi, mul(det(dj, sub(pi, pj)) / d, di));
+    }
+    const float2 nd = unit(sub(dj, di));
+    out.x = np.x;
+    out.y = np.y;
+    out.z = nd.x;
+    out.w = nd.y;
+    return true;
+  }
+};
+
 // LP3: minimise the maximum violation of the agent lines [n_obst, n), obstacle lines hard.
-// `P` is scratch line storage for the projected programme (at least n entries).  Lanes with
-// need = false only take part in the votes.
+// Lanes with need = false only take part in the votes.
+template <class LS>
+ORCA_HD void lp3(unsigned mask, bool need, const LS& L, int n, int n_obst, int begin, float radius, float2& result) {
+  float distance = 0.f;
+  int i = begin;
+  bool active = need;
+  while (ORCA_ANY(mask, active)) {
+    ProjectedLines<LS> V;
+    V.L = L;
+    V.pi = v2(0.f, 0.f);
+    V.di = v2(0.f, 0.f);
+    V.n_obst = n_obst;
+    if (active) {
+      while (i < n) {
+        const float4 li = L.get(i);
+        V.pi = pt(li);
+        V.di = dr(li);
+        if (det(V.di, sub(V.pi, result)) > distance) break;
+        ++i;
+      }
+      active = i < n;
+      if (active) ORCA_COUNT(0, 1);  // lp3 rounds
+    }
+    ORCA_CONVERGE(mask);
+    // the programme: every obstacle line, then the projections of agent lines [n_obst, i)
+    const int m = active ? (i > n_obst ? i : n_obst) : 0;
+    float2 cand = result;
+    const int f = lp2(mask, active, V, m, radius, v2(-V.di.y, V.di.x), true, cand);
+    if (active) {
+      if (!(f < m)) result = cand;  // on failure keep the previous result
+      distance = det(V.di, sub(V.pi, result));
+      ++i;
+    }
+  }
+}
+
+// LP3 with the projected programme materialised in scratch storage P (shared memory in
+// lp3_queue_kernel, where it is free): the projections are computed once per round instead of
+// once per access.  Same arithmetic, same results as lp3().
 template <class LS, class PS>
-ORCA_HD void lp3(unsigned mask, bool need, const LS& L, int n, int n_obst, int begin, float radius, const PS& P,
-                 float2& result) {
+ORCA_HD void lp3_stored(unsigned mask, bool need, const LS& L, int n, int n_obst, int begin, float radius, const PS& P,
+                        float2& result) {
   float distance = 0.f;
   int i = begin;
   bool active = need;
@@ -261,24 +345,15 @@ ORCA_HD void lp3(unsigned mask, bool need, const LS& L, int n, int n_obst, int b
     ORCA_CONVERGE(mask);
     int m = 0;
     if (active) {
-      ORCA_COUNT(0, 1);  // lp3 rounds
-      for (int j = 0; j < n_obst; ++j) {
-        const float4 lj = L.get(j);
-        P.set(m++, pt(lj), dr(lj));
-      }
-      for (int j = n_obst; j < i; ++j) {
-        const float4 lj = L.get(j);
-        const float2 pj = pt(lj), dj = dr(lj);
-        const float d = det(di, dj);
-        float2 np;
-        if (fabsf(d) <= kEps) {
-          if (dot(di, dj) > 0.f) continue;
-          np = mul(0.5f, add(pi, pj));
-        } else {
-          np = add(pi, mul(det(dj, sub(pi, pj)) / d, di));
-        }
-        P.set(m++, np, unit(sub(dj, di)));
-        ORCA_COUNT(1, 1);  // projected lines
+      ProjectedLines<LS> V;
+      V.L = L;
+      V.pi = pi;
+      V.di = di;
+      V.n_obst = n_obst;
+      const int hi = i > n_obst ? i : n_obst;
+      for (int j = 0; j < hi; ++j) {
+        float4 lj;
+        if (V.fetch(j, lj)) P.set(m++, pt(lj), dr(lj));
       }
     }
     ORCA_CONVERGE(mask);

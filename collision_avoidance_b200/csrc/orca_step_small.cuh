@@ -87,19 +87,6 @@ struct StepArgs {
   int grid_path;
 };
 
-struct LocalLines {  // LP3 scratch in local memory (rarely touched; lives in L1)
-  float4* base;
-  ORCA_HD float4 get(int i) const { return base[i]; }
-  ORCA_HD void set(int i, float2 point, float2 dir) const {
-    float4 v;
-    v.x = point.x;
-    v.y = point.y;
-    v.z = dir.x;
-    v.w = dir.y;
-    base[i] = v;
-  }
-};
-
 // Where an agent's neighbor candidates come from.  TileSource: the pre-step snapshot of the
 // agent's own env in shared memory, candidates = every other agent of the env in id order.
 struct TileSource {
@@ -376,10 +363,7 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
   c.p = p;
   c.v = v;
   if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, L, warp_mask, c)) return;
-  float4 proj[K + ORCA_MAX_OBST_LINES];
-  LocalLines P;
-  P.base = proj;
-  lp3(warp_mask, c.fail < c.n, L, c.n, c.n_obst, c.fail, a.vmax, P, c.nv);
+  lp3(warp_mask, c.fail < c.n, L, c.n, c.n_obst, c.fail, a.vmax, c.nv);
   agent_back<POLICY>(a, env, la, g, estep, c);
 }
 
@@ -427,11 +411,8 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
     Lines L;
     L.base = s_lines + tid;
     L.stride = blockDim.x;
-    float4 proj[K + ORCA_MAX_OBST_LINES];
-    LocalLines P;
-    P.base = proj;
     float2 nv = c.nv;
-    lp3(0xffffffffu, need, L, c.n, c.n_obst, c.fail, vmax, P, nv);
+    lp3(0xffffffffu, need, L, c.n, c.n_obst, c.fail, vmax, nv);
     s_nv[tid] = nv;
     __syncwarp();
     return;
@@ -467,7 +448,7 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
       P.base = s_pool + tid;
       P.stride = pool;
       float2 nv = s_nv[owner];
-      lp3(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, P, nv);
+      lp3_stored(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, P, nv);
       if (mine) s_nv[owner] = nv;
     }
   }
@@ -480,11 +461,8 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
     Lines L;
     L.base = s_lines + owner;
     L.stride = blockDim.x;
-    float4 proj[K + ORCA_MAX_OBST_LINES];
-    LocalLines P;
-    P.base = proj;
     float2 nv = s_nv[owner];
-    lp3(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, P, nv);
+    lp3(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, nv);
     if (mine) s_nv[owner] = nv;
   }
 #endif
