@@ -158,6 +158,28 @@ def cpu_baseline(steps: int, warmup: int, target_seconds: float = 12.0, threads:
     }
 
 
+def cpu_python_driver_baseline(steps: int = 30, envs: int = 8):
+    """The reference's own call pattern on one core: per agent setAgentPrefVelocity, one doStep,
+    per agent getAgentPosition/getAgentVelocity, all through Python (collision_avoidence_env.py
+    :371-400), with the oracle standing in for rvo2.  This is what "Python-RVO2 as the reference
+    uses it" costs; reported next to the C++-driver figure."""
+    from collision_avoidance_b200 import scenarios
+    from oracle.shell_oracle import AlanShellOracle
+    scn = scenarios.circle(envs, AGENTS, seed=SEED)
+    shells = [AlanShellOracle(scn, e) for e in range(envs)]
+    for sh in shells:
+        sh.orca_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for sh in shells:
+            sh.orca_step()
+            sh.step_count += 1
+            sh.done_test()
+    dt = time.perf_counter() - t0
+    return {"value": envs * AGENTS * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{envs} envs x {AGENTS} agents x {steps} steps, Python per-agent call pattern over the oracle"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  rvo2
     (Python-RVO2) is not available offline, so this times the oracle port of it (oracle/)
@@ -318,6 +340,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.steps, args.warmup)
+            line["cpu_baseline_python_driver"] = cpu_python_driver_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -114,6 +114,8 @@ void fill_common(const OrcaSim* s, orca::StepArgs* a) {
   a->env_nodes = s->per_env ? s->d_env_nodes : nullptr;
   a->shared_nodes = s->shared_nodes;
   a->vert_stride = s->per_env ? s->vert_stride : 0;
+  a->world_verts = s->vert_stride;
+  a->world_slots = 0;
 }
 
 template <int K, bool KFULL, int POLICY>
@@ -129,11 +131,14 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   orca::StepArgs args = a;
   args.envs_per_block = tpb / N;
   const int blocks = (s->E + args.envs_per_block - 1) / args.envs_per_block;
-  const size_t smem = orca::step_smem_bytes(K, tpb, true);
+  // obstacle tables staged in shared memory when they are small (<= 256 vertex slots = 16 KB)
+  const int slots = s->per_env ? args.envs_per_block * s->vert_stride : s->vert_stride;
+  args.world_slots = (slots > 0 && slots <= 256) ? slots : 0;
+  const size_t smem = orca::step_smem_bytes(K, tpb, true, args.world_slots);
   auto kern = orca::step_small_kernel<K, KFULL, POLICY>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::step_smem_bytes(K, 256, true)));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::step_smem_bytes(K, 256, true, 256)));
     attr_set = true;
   }
   kern<<<blocks, tpb, smem, st>>>(args);

@@ -142,10 +142,12 @@ struct ObstacleWorld {
 };
 
 #if defined(__CUDA_ARCH__)
-#define ORCA_LDG(p) __ldg(p)
+#define ORCA_LDG(p) __ldg(p)  // read-only global data
 #else
 #define ORCA_LDG(p) (*(p))
 #endif
+// obstacle tables may sit in global OR shared memory (staged by the tile kernel): generic load
+#define ORCA_LD(p) (*(p))
 
 // ---- linear programs -------------------------------------------------------------
 // The LPs read their constraints through a "line source" S: S.fetch(j, out) yields virtual line j
@@ -539,8 +541,8 @@ ORCA_HD void obstacle_neighbors(const ObstacleWorld& W, float2 p, float range_sq
     while (sp > 0) {
       const int top = stk[sp - 1];
       const int node = top >> 1;
-      const int4 nd = ORCA_LDG(&W.bsp[node]);
-      const float4 sg = ORCA_LDG(&W.bsp_seg[node]);
+      const int4 nd = ORCA_LD(&W.bsp[node]);
+      const float4 sg = ORCA_LD(&W.bsp_seg[node]);
       const int v1 = nd.x;
       const float2 p1 = v2(sg.x, sg.y), p2 = v2(sg.z, sg.w);
       const float side = left_of(p1, p2, p);
@@ -599,11 +601,11 @@ ORCA_HD int obstacle_lines(const ObstacleWorld& W, float2 p, float2 vel, float r
   const float r_sq = sqr(radius);
   for (int q = 0; q < cnt; ++q) {
     int o1 = oid[q];
-    float4 a = ORCA_LDG(&W.vert_pd[o1]);
-    int4 la = ORCA_LDG(&W.vert_link[o1]);
+    float4 a = ORCA_LD(&W.vert_pd[o1]);
+    int4 la = ORCA_LD(&W.vert_link[o1]);
     int o2 = la.x;
-    float4 b = ORCA_LDG(&W.vert_pd[o2]);
-    int4 lb = ORCA_LDG(&W.vert_link[o2]);
+    float4 b = ORCA_LD(&W.vert_pd[o2]);
+    int4 lb = ORCA_LD(&W.vert_link[o2]);
     float2 p1 = v2(a.x, a.y), p2 = v2(b.x, b.y);
     float2 dir1 = v2(a.z, a.w), dir2 = v2(b.z, b.w);
     bool cvx1 = la.z != 0, cvx2 = lb.z != 0;
@@ -697,7 +699,7 @@ ORCA_HD int obstacle_lines(const ObstacleWorld& W, float2 p, float2 vel, float r
         // a leg may not point into the neighboring edge of a convex vertex: use that edge's
         // cut-off line instead and remember that the leg is "foreign"
         const int left_nbr = la.y;  // obstacle1->prev
-        const float4 ln = ORCA_LDG(&W.vert_pd[left_nbr]);
+        const float4 ln = ORCA_LD(&W.vert_pd[left_nbr]);
         const float2 ln_dir = v2(ln.z, ln.w);
         bool left_foreign = false, right_foreign = false;
         if (cvx1 && det(left_leg, neg(ln_dir)) >= 0.f) {

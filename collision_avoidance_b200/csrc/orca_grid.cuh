@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128, 6) step_grid_kernel(const StepArgs a, con
     L.stride = tpb;
     c.p = spos[j];
     c.v = svel[j];
-    alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, L, warp_mask, c);
+    alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
   block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);

@@ -80,6 +80,8 @@ struct StepArgs {
   const int* env_nodes;  // per-env node count, or NULL when the world is shared
   int shared_nodes;      // node count of the shared world
   int vert_stride;       // per-env table stride (0 when shared)
+  int world_slots;       // vertex slots of the obstacle tables a block stages in shared memory (0: read global)
+  int world_verts;       // number of rows in one obstacle table (shared world: its vertex count)
   // 1: stop after the neighbor search (orca_neighbors parity hook)
   int neighbors_only;
   // 1: uniform-grid path; an env spans several blocks, so its step counter is bumped by a
@@ -167,12 +169,24 @@ struct AgentCarry {
   bool overflow;
 };
 
+// The obstacle tables of env `env` as they sit in global memory.
+ORCA_HD ObstacleWorld global_world(const StepArgs& a, int env) {
+  ObstacleWorld W;
+  const size_t voff = (size_t)env * a.vert_stride;
+  W.vert_pd = a.vert_pd + voff;
+  W.vert_link = a.vert_link + voff;
+  W.bsp = a.bsp + voff;
+  W.bsp_seg = a.bsp_seg + voff;
+  W.n_nodes = (a.env_nodes != nullptr) ? a.env_nodes[env] : a.shared_nodes;
+  return W;
+}
+
 // Front half.  `src` yields the PRE-step state of the other agents (shared-memory tile or
 // uniform-grid cells), `L` is the agent's private line storage, `estep` the env's step counter
 // before this step.  Returns false when the step ends here (neighbors-only parity hook).
 template <int K, bool KFULL, int POLICY, class Src>
 ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const int estep, const Src& src,
-                         const Lines L, const unsigned warp_mask, AgentCarry& c) {
+                         const ObstacleWorld& W, const Lines L, const unsigned warp_mask, AgentCarry& c) {
   const float2 p = c.p, v = c.v;
 
   // ---------------- preferred velocity (policy) ----------------
@@ -229,15 +243,6 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
   c.act = act;
 
   // ---------------- neighbors ----------------
-  ObstacleWorld W;
-  {
-    const size_t voff = (size_t)env * a.vert_stride;
-    W.vert_pd = a.vert_pd + voff;
-    W.vert_link = a.vert_link + voff;
-    W.bsp = a.bsp + voff;
-    W.bsp_seg = a.bsp_seg + voff;
-    W.n_nodes = (a.env_nodes != nullptr) ? a.env_nodes[env] : a.shared_nodes;
-  }
   bool overflow = false;
   float od[ORCA_MAX_OBST_NEIGHBORS];
   int oid[ORCA_MAX_OBST_NEIGHBORS];
@@ -362,7 +367,7 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
   AgentCarry c;
   c.p = p;
   c.v = v;
-  if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, L, warp_mask, c)) return;
+  if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c)) return;
   lp3(warp_mask, c.fail < c.n, L, c.n, c.n_obst, c.fail, a.vmax, c.nv);
   agent_back<POLICY>(a, env, la, g, estep, c);
 }
@@ -381,8 +386,9 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
 #define ORCA_LP3_SMEM_POOL 0
 #endif
 // dynamic shared memory of the step kernels: [pos|vel tile (tile path only)] + lines + LP3 queue
-inline size_t step_smem_bytes(int K, int tpb, bool tile) {
-  size_t b = (size_t)tpb * ((tile ? 16 : 0) + (size_t)(K + ORCA_MAX_OBST_LINES) * 16 + 8 + 4 + 2) + 32 * 4;
+inline size_t step_smem_bytes(int K, int tpb, bool tile, int world_slots = 0) {
+  size_t b = (size_t)world_slots * 64 + 16;  // staged obstacle tables: 4 x 16 B per vertex slot
+  b += (size_t)tpb * ((tile ? 16 : 0) + (size_t)(K + ORCA_MAX_OBST_LINES) * 16 + 8 + 4 + 2) + 32 * 4;
 #if ORCA_LP3_SMEM_POOL
   b += (size_t)(tpb / 2) * (K + ORCA_MAX_OBST_LINES) * 16 + 16;  // LP3 projected-line pool
 #endif
@@ -483,6 +489,8 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   int* s_meta = reinterpret_cast<int*>(s_nv + tpb);
   int* s_warp_cnt = s_meta + tpb;
   unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_warp_cnt + 32);
+  // staged obstacle tables (16-byte aligned, after the queue): vert_pd | vert_link | bsp | bsp_seg
+  float4* s_world = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(s_queue + tpb) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x;
   const int N = a.N;
@@ -505,10 +513,34 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
     s_vel[tid] = c.v;
     if (a.env_step != nullptr) estep = a.env_step[env];
   }
+  // The BSP walk is a chain of dependent node loads done by every agent every step: from global
+  // memory each hop is an L2 round trip.  The tables are tiny (64 B per vertex), so the block
+  // copies the ones of its envs into shared memory first.
+  const int slots = a.world_slots;
+  if (slots > 0) {
+    const size_t first = (size_t)blockIdx.x * a.envs_per_block * a.vert_stride;  // 0 for a shared world
+    const size_t limit = (a.vert_stride > 0) ? (size_t)a.E * a.vert_stride : (size_t)a.world_verts;
+    for (int s = tid; s < slots; s += tpb) {
+      if (first + s < limit) {
+        s_world[s] = a.vert_pd[first + s];
+        s_world[slots + s] = *reinterpret_cast<const float4*>(&a.vert_link[first + s]);
+        s_world[2 * slots + s] = *reinterpret_cast<const float4*>(&a.bsp[first + s]);
+        s_world[3 * slots + s] = a.bsp_seg[first + s];
+      }
+    }
+  }
   __syncthreads();
   const unsigned warp_mask = __ballot_sync(0xffffffffu, valid);  // lanes that run the step
   bool alive = valid;
   if (valid) {
+    ObstacleWorld W = global_world(a, env);
+    if (slots > 0) {
+      const int off = le * a.vert_stride;  // 0 for a shared world
+      W.vert_pd = s_world + off;
+      W.vert_link = reinterpret_cast<const int4*>(s_world + slots) + off;
+      W.bsp = reinterpret_cast<const int4*>(s_world + 2 * slots) + off;
+      W.bsp_seg = s_world + 3 * slots + off;
+    }
     Lines L;
     L.base = s_lines + tid;
     L.stride = tpb;
@@ -517,7 +549,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
     src.env_vel = s_vel + le * N;
     src.n = N;
     src.self = la;
-    alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, L, warp_mask, c);
+    alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, W, L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
   block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);
