@@ -67,8 +67,38 @@ ORCA_HD float4 observe_ray(const ObsArgs& a, int g, int ray) {
   float best = INFINITY;
   float2 best_hit = v2(0.f, 0.f), best_vel = v2(0.f, 0.f);
 
+  // A neighbor polygon is inscribed in the circle of radius |poly[0]| around the neighbor, so a
+  // ray that stays farther than that from the centre cannot hit any of its segments.  Each lane
+  // (= ray) first collects the neighbors it can hit at all (typically 1-2 of 5) in a bit mask and
+  // then walks only those: lanes of a warp work on DIFFERENT neighbors in the same iteration, so
+  // the culling survives SIMT (a plain `continue` would not: some ray always hits).  The bound is
+  // padded far beyond float32 rounding of the vertex positions, so no hit is ever dropped.
   const int cnt = a.nbr_cnt[g];
-  for (int q = 0; q < cnt; ++q) {
+  unsigned todo = 0u;
+  {
+    const float ray_len = sqrtf(e.x * e.x + e.y * e.y);
+    const float inv_len = 1.0f / ray_len;
+    const float2 u = v2(e.x * inv_len, e.y * inv_len);
+    const float reach = sqrtf(a.poly[0].x * a.poly[0].x + a.poly[0].y * a.poly[0].y) * 1.001f + 1e-4f;
+    for (int q = 0; q < cnt; ++q) {
+      const int j = env * a.N + a.nbr_idx[(size_t)g * a.k + q];
+      const float2 rel = sub(a.pos[j], p);
+      const float2 ctr = v2(c * rel.x - s * rel.y, s * rel.x + c * rel.y);
+      const float along = ctr.x * u.x + ctr.y * u.y;
+      const float perp_sq = (ctr.x * ctr.x + ctr.y * ctr.y) - along * along;
+      if (along >= -reach && along <= ray_len + reach && perp_sq <= reach * reach) todo |= 1u << q;
+    }
+  }
+  // neighbors are visited in list order (lowest bit first) and ties keep the first minimum, so the
+  // winner is the same as when every neighbor is tested
+  while (todo != 0u) {
+#if defined(__CUDA_ARCH__)
+    const int q = __ffs(todo) - 1;
+#else
+    int q = 0;
+    while (!((todo >> q) & 1u)) ++q;
+#endif
+    todo &= todo - 1u;
     const int j = env * a.N + a.nbr_idx[(size_t)g * a.k + q];
     const float2 rel = sub(a.pos[j], p);
     const float2 nv = a.vel[j];
