@@ -33,7 +33,7 @@ MAX_ACTIONS = 16
 EXPORTED_SYMBOLS = (
     "orca_abi_version", "orca_last_error", "orca_create", "orca_destroy", "orca_get_params",
     "orca_set_obstacles", "orca_obstacle_vertex_count", "orca_get_obstacle_vertices",
-    "orca_step", "orca_env_step", "orca_neighbors", "orca_observe", "orca_step_host", "orca_launch_count",
+    "orca_step", "orca_env_step", "orca_env_step_many", "orca_neighbors", "orca_observe", "orca_step_host", "orca_launch_count",
 )
 
 
@@ -120,6 +120,7 @@ def load() -> ctypes.CDLL:
     L.orca_get_obstacle_vertices.argtypes = [hp, i, _vp, _vp, _vp, _vp]
     L.orca_step.argtypes = [hp, _vp, _vp, _vp, _vp]
     L.orca_env_step.argtypes = [hp, ctypes.POINTER(OrcaEnvStepArgs), _vp]
+    L.orca_env_step_many.argtypes = [hp, ctypes.POINTER(OrcaEnvStepArgs), i, _vp]
     L.orca_neighbors.argtypes = [hp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.orca_observe.argtypes = [hp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, i, i, _vp, _vp]
     L.orca_step_host.argtypes = [hp, _vp, _vp, _vp, i, i, i]

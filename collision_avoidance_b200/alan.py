@@ -137,9 +137,10 @@ class Collision_Avoidance_Sim:
         self._init_world()
 
     # ------------------------------------------------------------------ steps
-    def online_step(self, uniforms: Optional[torch.Tensor] = None):
+    def online_step(self, uniforms: Optional[torch.Tensor] = None, steps: int = 1):
         """ALAN_true.py:569-628 for every world.  ``uniforms`` ([E, N] in [0, 1)) overrides the
-        in-kernel Philox draw (parity tests)."""
+        in-kernel Philox draw (parity tests).  ``steps`` > 1 issues that many steps back to back
+        from C without returning to Python."""
         self.sim.env_step(policy=_lib.POLICY_ALAN, goal=self.goal, goal2=self.goal2, done_mode=_lib.DONE_GOAL_RADIUS,
                           alan_weights=self.action_weights, alan_actions=self.action_table,
                           alan_action_out=self.action_ids, alan_uniform=uniforms,
@@ -147,13 +148,13 @@ class Collision_Avoidance_Sim:
                           alan_window_steps=self.window_steps, alan_gamma=self.gamma, alan_temp=self.online_temp,
                           rng_seed=self.seed * 1_000_003 + self._episode, reward=self.reward,
                           agent_done=self.agents_done, arrival_time=self.agents_time, env_step=self.env_step,
-                          env_done_cnt=self.env_done_cnt)
+                          env_done_cnt=self.env_done_cnt, steps=steps)
 
-    def orca_step(self):
+    def orca_step(self, steps: int = 1):
         """ALAN_true.py:631-636 for every world (doStep, then goal-directed preferred velocity)."""
         self.sim.env_step(policy=_lib.POLICY_GOAL, goal=self.goal, goal2=self.goal2, done_mode=_lib.DONE_GOAL_RADIUS,
                           agent_done=self.agents_done, arrival_time=self.agents_time, env_step=self.env_step,
-                          env_done_cnt=self.env_done_cnt)
+                          env_done_cnt=self.env_done_cnt, steps=steps)
 
     def done_test(self) -> torch.Tensor:
         """ALAN_true.py:547-566.  The test itself ran inside the last step; this returns the
@@ -167,13 +168,16 @@ class Collision_Avoidance_Sim:
         if mode not in (0, 1):
             mode = 1
         limit = self.max_step if max_steps is None else int(max_steps)
-        for i in range(limit):
+        done_steps = 0
+        while done_steps < limit:
+            chunk = min(check_every, limit - done_steps)
             if mode == 1:
-                self.online_step()
+                self.online_step(steps=chunk)
             else:
-                self.orca_step()
-            self.step_count += 1
-            if (i + 1) % check_every == 0 and bool(self.done_test().all()):
+                self.orca_step(steps=chunk)
+            done_steps += chunk
+            self.step_count += chunk
+            if bool(self.done_test().all()):
                 break
         success = self.done_test()
         times = self.agents_time.double()

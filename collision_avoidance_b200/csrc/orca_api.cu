@@ -417,6 +417,17 @@ int orca_env_step(OrcaSim* s, const OrcaEnvStepArgs* in, void* stream) {
   return launch_step(s, a, in->policy, static_cast<cudaStream_t>(stream));
 }
 
+int orca_env_step_many(OrcaSim* s, const OrcaEnvStepArgs* in, int steps, void* stream) {
+  if (steps < 1) return fail(ORCA_ERR_INVALID, "steps must be >= 1");
+  if (in != nullptr && in->alan_uniform_in_dev != nullptr && steps > 1)
+    return fail(ORCA_ERR_INVALID, "externally supplied uniforms cover a single step");
+  for (int t = 0; t < steps; ++t) {
+    const int rc = orca_env_step(s, in, stream);
+    if (rc != ORCA_OK) return rc;
+  }
+  return ORCA_OK;
+}
+
 int orca_neighbors(OrcaSim* s, const float* pos_dev, int32_t* nbr_idx_dev, float* nbr_distsq_dev, int32_t* nbr_cnt_dev,
                    int32_t* obst_nbr_idx_dev, int32_t* obst_nbr_cnt_dev, void* stream) {
   if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");

@@ -439,41 +439,49 @@ struct NearestK {
     for (int s = 1; s < K; ++s) m = fmaxf(m, d[s]);
     return m;
   }
+  // Stable sorted insert.  "the candidate goes in front of slot s" is monotone in s because the
+  // list is sorted, so every entry from the first such slot on moves up by one and keeps its
+  // relative order (RVO2 shifts while distSq < prev.first).  Every slot is compared with the
+  // CANDIDATE (not with a carried element), so the K comparisons are independent of each other.
   // Candidates arrive in ascending id: equal distances keep the earlier entry in front.
   ORCA_HD void offer(float cand_d, int cand_id) {
     if (cand_d < thresh()) {
-      float cd = cand_d;
-      int ci = cand_id;
+      bool prev_before = false;  // did the candidate go in front of slot s - 1 ?
+      float prev_d = cand_d;     // old content of slot s - 1
+      int prev_i = cand_id;
 #pragma unroll
       for (int s = 0; s < K; ++s) {
-        const bool sw = cd < d[s];
-        const float td = d[s];
-        const int ti = id[s];
-        d[s] = sw ? cd : td;
-        id[s] = sw ? ci : ti;
-        cd = sw ? td : cd;
-        ci = sw ? ti : ci;
+        const bool before = cand_d < d[s];
+        const float old_d = d[s];
+        const int old_i = id[s];
+        d[s] = before ? (prev_before ? prev_d : cand_d) : old_d;
+        id[s] = before ? (prev_before ? prev_i : cand_id) : old_i;
+        prev_before = before;
+        prev_d = old_d;
+        prev_i = old_i;
       }
     }
   }
   // Candidates arrive in arbitrary order (uniform-grid cells): order by (distance, rank) where
-  // `before(a, b)` says whether entry a precedes entry b at equal distance (b may be -1 = empty
+  // `precedes(a, b)` says whether entry a goes before entry b at equal distance (b may be -1 = empty
   // slot, which nothing precedes).  Gives the same list as ascending-id visiting.
   template <class Before>
-  ORCA_HD void offer_ranked(float cand_d, int cand_id, const Before& before) {
+  ORCA_HD void offer_ranked(float cand_d, int cand_id, const Before& precedes) {
     if (cand_d <= thresh()) {
-      float cd = cand_d;
-      int ci = cand_id;
+      bool prev_before = false;
+      float prev_d = cand_d;
+      int prev_i = cand_id;
 #pragma unroll
       for (int s = 0; s < K; ++s) {
-        bool sw = cd < d[s];
-        if (cd == d[s]) sw = before(ci, id[s]);
-        const float td = d[s];
-        const int ti = id[s];
-        d[s] = sw ? cd : td;
-        id[s] = sw ? ci : ti;
-        cd = sw ? td : cd;
-        ci = sw ? ti : ci;
+        bool before = cand_d < d[s];
+        if (cand_d == d[s]) before = precedes(cand_id, id[s]);
+        const float old_d = d[s];
+        const int old_i = id[s];
+        d[s] = before ? (prev_before ? prev_d : cand_d) : old_d;
+        id[s] = before ? (prev_before ? prev_i : cand_id) : old_i;
+        prev_before = before;
+        prev_d = old_d;
+        prev_i = old_i;
       }
     }
   }

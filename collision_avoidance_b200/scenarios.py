@@ -68,7 +68,7 @@ def circle(num_envs: int, num_agents: int, seed: int = 0, radius: float = 0.5, r
     R = circumference / (2 * pi)
     envsize = 2 * R + 4 * radius
     theta = np.arange(num_agents) * ((2 * pi) / num_agents)
-    theta = theta[None, :] + (rng.uniform(0, 2 * pi, size=(num_envs, 1)) if rotate else 0.0)
+    theta = theta[None, :] + (rng.uniform(0, 2 * pi, size=(num_envs, 1)) if rotate else np.zeros((num_envs, 1)))
     c = envsize / 2
     pos = np.stack([c + R * np.cos(theta), c + R * np.sin(theta)], -1)
     goal = np.stack([c + R * np.cos(theta + pi), c + R * np.sin(theta + pi)], -1)

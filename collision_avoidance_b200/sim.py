@@ -189,7 +189,7 @@ class BatchedRVOSimulator:
                  reward: Optional[torch.Tensor] = None, agent_done: Optional[torch.Tensor] = None,
                  arrival_time: Optional[torch.Tensor] = None, env_step: Optional[torch.Tensor] = None,
                  env_done_cnt: Optional[torch.Tensor] = None, want_neighbors: bool = False,
-                 collect_stats: bool = True):
+                 collect_stats: bool = True, steps: int = 1):
         """One fused step: policy -> doStep -> reward -> done test -> bandit update (orca_env_step)."""
         E, N = self.num_envs, self.agents_per_env
         a = _lib.OrcaEnvStepArgs()
@@ -250,7 +250,10 @@ class BatchedRVOSimulator:
             a.obst_nbr_idx_dev, a.obst_nbr_cnt_dev = self.obst_nbr_idx.data_ptr(), self.obst_nbr_cnt.data_ptr()
         if collect_stats:
             a.stats_dev = self.stats.data_ptr()
-        _lib.check(self._L.orca_env_step(self._h, ctypes.byref(a), self._stream()))
+        if steps == 1:
+            _lib.check(self._L.orca_env_step(self._h, ctypes.byref(a), self._stream()))
+        else:  # back-to-back launches issued from C (orca_env_step_many): no Python in between
+            _lib.check(self._L.orca_env_step_many(self._h, ctypes.byref(a), int(steps), self._stream()))
 
     # ------------------------------------------------------------------ observation
     def observe(self, goal: torch.Tensor, obs: Optional[torch.Tensor] = None, laser_num: int = 16,

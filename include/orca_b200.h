@@ -170,6 +170,10 @@ int orca_get_obstacle_vertices(const OrcaSim* sim, int env, float* xy_out, int32
 int orca_step(OrcaSim* sim, float* pos_dev, float* vel_dev, const float* pref_dev, void* stream);
 /* Fused environment step: policy + doStep + reward + done test + bandit update. */
 int orca_env_step(OrcaSim* sim, const OrcaEnvStepArgs* args, void* stream);
+/* `steps` fused environment steps back to back on `stream` without returning to the host in
+ * between (run_sim's inner loop, ALAN_true.py:113-121): removes the per-step host overhead that
+ * dominates small batches.  Same arguments as orca_env_step. */
+int orca_env_step_many(OrcaSim* sim, const OrcaEnvStepArgs* args, int steps, void* stream);
 /* Parity hook: neighbor search only.  nbr_distsq_dev optional. */
 int orca_neighbors(OrcaSim* sim, const float* pos_dev, int32_t* nbr_idx_dev, float* nbr_distsq_dev,
                    int32_t* nbr_cnt_dev, int32_t* obst_nbr_idx_dev, int32_t* obst_nbr_cnt_dev, void* stream);

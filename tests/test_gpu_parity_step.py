@@ -210,3 +210,39 @@ def test_grid_equals_tile_over_long_runs(monkeypatch):
     assert grid.launch_count() == 150 * 9 and tile.launch_count() == 150
     assert torch.equal(tile.pos, grid.pos) and torch.equal(tile.vel, grid.vel)
     assert tile.read_stats() == grid.read_stats()
+
+
+def test_exact_ties_keep_first_visited_order_on_gpu():
+    """Perfectly symmetric rings produce bit-equal distances.  With N <= 10 RVO2's kd-tree is one
+    leaf visited in id order, so the ORDERED neighbor lists (not just the sets) must be identical
+    to the oracle's, and so must the velocities."""
+    import torch
+    from collision_avoidance_b200 import scenarios
+    for N, k in ((10, 5), (10, 9), (8, 4)):
+        scn = scenarios.circle(3, N, seed=3, rotate=False)
+        scn.params = dict(scn.params, maxNeighbors=k)
+        c = scn.envsize / 2
+        d = c - scn.pos
+        scn.vel = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+        sims = oracle_sims(scn)
+        gpu = _gpu_sim(scn)
+        ties = 0
+        for _ in range(40):
+            pos = np.stack([s.positions() for s in sims])
+            vel = np.stack([s.velocities() for s in sims])
+            pref = goal_pref(pos, scn.goal).astype(np.float32)
+            for e, s in enumerate(sims):
+                s.set_pref_velocities(pref[e])
+                s.doStep()
+            gpu.pos.copy_(torch.from_numpy(pos))
+            gpu.vel.copy_(torch.from_numpy(vel))
+            gpu.pref.copy_(torch.from_numpy(pref))
+            idx, cnt, _, _ = [x.cpu().numpy() for x in gpu.neighbors()]
+            gpu.doStep()
+            for e in range(3):
+                for i in range(N):
+                    o = sims[e].agent_neighbors(i)
+                    ties += len(set(x[1] for x in o)) < len(o)
+                    assert [x[0] for x in o] == list(idx[e, i, :cnt[e, i]]), (N, k, e, i)
+            assert np.array_equal(gpu.vel.cpu().numpy(), np.stack([s.velocities() for s in sims]))
+        assert ties > 50

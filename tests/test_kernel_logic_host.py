@@ -92,3 +92,36 @@ def test_philox_twin():
     for seed, c0, c1 in [(0, 0, 0), (123456789012345, 17, 3), (2 ** 63 + 5, 1048575, 999)]:
         assert L.emul_philox_uniform(seed, c0, c1) == philox_uniform(seed, np.array([c0]), c1)[0]
         assert 0.0 <= L.emul_philox_uniform(seed, c0, c1) < 1.0
+
+
+def test_equal_distances_keep_first_visited_order():
+    """Exact ties (perfectly symmetric ring): the k-nearest list must be STABLE -- equal distances
+    stay in visiting (= id) order, also when a closer candidate is inserted in front of them.  With
+    N <= 10 the oracle's kd-tree is a single leaf visited in id order, so the ordered lists must be
+    identical, not just equal up to ties."""
+    for N, k in ((10, 5), (10, 9), (8, 4)):
+        scn = scenarios.circle(2, N, seed=3, rotate=False)
+        scn.params = dict(scn.params, maxNeighbors=k)
+        c = scn.envsize / 2
+        d = c - scn.pos
+        scn.vel = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+        P = snake(scn.params)
+        W = _emul.World(scn.obstacles)
+        sims = oracle_sims(scn)
+        ties = 0
+        for _ in range(40):
+            pos = np.stack([s.positions() for s in sims])
+            vel = np.stack([s.velocities() for s in sims])
+            pref = goal_pref(pos, scn.goal).astype(np.float32)
+            for e, s in enumerate(sims):
+                s.set_pref_velocities(pref[e])
+                s.doStep()
+            pe, ve = pos.copy(), vel.copy()
+            out = _emul.emul_step(P, pe, ve, policy=0, pref=np.ascontiguousarray(pref), world=W, want_neighbors=True)
+            for e in range(2):
+                for i in range(N):
+                    o = sims[e].agent_neighbors(i)
+                    ties += len(set(x[1] for x in o)) < len(o)
+                    assert [x[0] for x in o] == list(out["nbr_idx"][e, i, :out["nbr_cnt"][e, i]])
+            assert np.array_equal(ve, np.stack([s.velocities() for s in sims]))
+        assert ties > 50
