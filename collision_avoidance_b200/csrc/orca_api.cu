@@ -41,6 +41,19 @@ int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(ORCA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
   } while (0)
 
+// Switches to the handle's device for the duration of a call and restores the caller's device
+// afterwards (the caller -- torch -- must not find its current device changed).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = (cudaSetDevice(device) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 }  // namespace
 
 struct OrcaSim {
@@ -203,7 +216,7 @@ int orca_create(const OrcaParams* params, int device, int num_envs, int agents_p
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(ORCA_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);
   OrcaSim* s = new OrcaSim();
   s->p = *params;
   s->device = device;
@@ -220,7 +233,7 @@ int orca_create(const OrcaParams* params, int device, int num_envs, int agents_p
 
 int orca_destroy(OrcaSim* s) {
   if (s == nullptr) return ORCA_OK;
-  cudaSetDevice(s->device);
+  DeviceGuard guard(s->device);
   free_obstacles(s);
   cudaFree(s->d_pos);
   cudaFree(s->d_vel);
@@ -244,7 +257,7 @@ int orca_set_obstacles(OrcaSim* s, const float* xy, const int32_t* poly_sizes, i
   if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
   if (num_polys < 0 || (num_polys > 0 && (xy == nullptr || poly_sizes == nullptr)))
     return fail(ORCA_ERR_INVALID, "bad polygon arguments");
-  CUDA_TRY(cudaSetDevice(s->device));
+  DeviceGuard guard(s->device);
   free_obstacles(s);
   s->per_env = (polys_per_env != nullptr);
   const int n_worlds = s->per_env ? s->E : 1;
@@ -344,7 +357,7 @@ int orca_get_obstacle_vertices(const OrcaSim* s, int env, float* xy_out, int32_t
 int orca_step(OrcaSim* s, float* pos_dev, float* vel_dev, const float* pref_dev, void* stream) {
   if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
   if (pos_dev == nullptr || vel_dev == nullptr || pref_dev == nullptr) return fail(ORCA_ERR_INVALID, "null state pointer");
-  CUDA_TRY(cudaSetDevice(s->device));
+  DeviceGuard guard(s->device);
   orca::StepArgs a;
   fill_common(s, &a);
   a.pos = reinterpret_cast<float2*>(pos_dev);
@@ -381,7 +394,7 @@ int orca_env_step(OrcaSim* s, const OrcaEnvStepArgs* in, void* stream) {
   if (in->nbr_idx_dev != nullptr && in->nbr_cnt_dev == nullptr) return fail(ORCA_ERR_INVALID, "nbr_idx_dev needs nbr_cnt_dev");
   if (in->obst_nbr_idx_dev != nullptr && in->obst_nbr_cnt_dev == nullptr)
     return fail(ORCA_ERR_INVALID, "obst_nbr_idx_dev needs obst_nbr_cnt_dev");
-  CUDA_TRY(cudaSetDevice(s->device));
+  DeviceGuard guard(s->device);
   orca::StepArgs a;
   fill_common(s, &a);
   a.pos = reinterpret_cast<float2*>(in->pos_dev);
@@ -434,7 +447,7 @@ int orca_neighbors(OrcaSim* s, const float* pos_dev, int32_t* nbr_idx_dev, float
   if (pos_dev == nullptr || nbr_idx_dev == nullptr || nbr_cnt_dev == nullptr)
     return fail(ORCA_ERR_INVALID, "pos_dev, nbr_idx_dev and nbr_cnt_dev are required");
   if (obst_nbr_idx_dev != nullptr && obst_nbr_cnt_dev == nullptr) return fail(ORCA_ERR_INVALID, "obst_nbr_idx_dev needs obst_nbr_cnt_dev");
-  CUDA_TRY(cudaSetDevice(s->device));
+  DeviceGuard guard(s->device);
   orca::StepArgs a;
   fill_common(s, &a);
   // the search only reads positions; velocities alias them and nothing is written back
@@ -459,7 +472,7 @@ int orca_observe(OrcaSim* s, const float* pos_dev, const float* vel_dev, const f
   if (laser_num < 1 || laser_num > ORCA_MAX_LASER) return fail(ORCA_ERR_UNSUPPORTED, "laser_num must be in [1, %d]", ORCA_MAX_LASER);
   if (circle_approx_num < 3 || circle_approx_num > ORCA_MAX_CIRCLE_APPROX)
     return fail(ORCA_ERR_UNSUPPORTED, "circle_approx_num must be in [3, %d]", ORCA_MAX_CIRCLE_APPROX);
-  CUDA_TRY(cudaSetDevice(s->device));
+  DeviceGuard guard(s->device);
   orca::ObsArgs a;
   std::memset(&a, 0, sizeof(a));
   a.E = s->E;
@@ -505,7 +518,7 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
   if (policy != ORCA_POLICY_EXTERNAL && policy != ORCA_POLICY_GOAL)
     return fail(ORCA_ERR_INVALID, "orca_step_host supports the EXTERNAL and GOAL policies");
   if (steps < 1) return fail(ORCA_ERR_INVALID, "steps must be >= 1");
-  CUDA_TRY(cudaSetDevice(s->device));
+  DeviceGuard guard(s->device);
   int rc = ensure_host_staging(s);
   if (rc != ORCA_OK) return rc;
   const size_t bytes = (size_t)s->E * s->N * sizeof(float2);
