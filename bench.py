@@ -296,8 +296,9 @@ def run_ours(args):
     pos_h = torch.from_numpy(scn.pos.copy()).pin_memory()
     vel_h = torch.from_numpy(scn.vel.copy()).pin_memory()
     goal_h = torch.from_numpy(scn.goal.copy()).pin_memory()
-    e2e_steps = max(3, min(args.steps, 50))
-    sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=1)
+    # same episode phase as the kernel-timed region: W steps from the reset state, then K timed
+    e2e_steps = max(3, args.steps)
+    sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=max(1, args.warmup))
     for _ in range(2):
         sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
     barrier()
@@ -332,7 +333,7 @@ def run_ours(args):
                          "note": "kernel is FP32-issue bound, not HBM bound; see DESIGN.md Roofline"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_state,
                     "d2h_bytes_per_step": 2 * bytes_state, "steps": e2e_steps,
-                    "api": "BatchedRVOSimulator.step_host -> orca_step_host (pinned host buffers)"},
+                    "api": "BatchedRVOSimulator.step_host -> orca_step_host (pinned host buffers; env chunks pipelined over streams: upload | step | download)"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "wall_s_timed_region": wall,

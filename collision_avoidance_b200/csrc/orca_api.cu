@@ -6,6 +6,7 @@
 // -fmad=false is part of the contract: see orca_core.cuh.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -56,6 +57,10 @@ struct DeviceGuard {
 
 }  // namespace
 
+// orca_step_host pipelining: at most this many env chunks, of about this many agents each
+constexpr int kHostChunksMax = 16;
+constexpr long long kHostChunkAgents = 131072;
+
 struct OrcaSim {
   OrcaParams p{};
   int device = 0;
@@ -75,7 +80,7 @@ struct OrcaSim {
   float2* d_pos = nullptr;
   float2* d_vel = nullptr;
   float2* d_aux = nullptr;
-  cudaStream_t host_stream = nullptr;
+  cudaStream_t host_streams[kHostChunksMax] = {};
   // uniform-grid scratch (large worlds)
   orca::GridScratch grid;
   int64_t launches = 0;
@@ -143,7 +148,7 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   }
   orca::StepArgs args = a;
   args.envs_per_block = tpb / N;
-  const int blocks = (s->E + args.envs_per_block - 1) / args.envs_per_block;
+  const int blocks = (a.E - a.env_base + args.envs_per_block - 1) / args.envs_per_block;
   // obstacle tables staged in shared memory when they are small (<= 256 vertex slots = 16 KB)
   const int slots = s->per_env ? args.envs_per_block * s->vert_stride : s->vert_stride;
   args.world_slots = (slots > 0 && slots <= 256) ? slots : 0;
@@ -193,7 +198,7 @@ int ensure_host_staging(OrcaSim* s) {
   CUDA_TRY(cudaMalloc(&s->d_pos, bytes));
   CUDA_TRY(cudaMalloc(&s->d_vel, bytes));
   CUDA_TRY(cudaMalloc(&s->d_aux, bytes));
-  CUDA_TRY(cudaStreamCreateWithFlags(&s->host_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < kHostChunksMax; ++c) CUDA_TRY(cudaStreamCreateWithFlags(&s->host_streams[c], cudaStreamNonBlocking));
   return ORCA_OK;
 }
 
@@ -238,7 +243,8 @@ int orca_destroy(OrcaSim* s) {
   cudaFree(s->d_pos);
   cudaFree(s->d_vel);
   cudaFree(s->d_aux);
-  if (s->host_stream) cudaStreamDestroy(s->host_stream);
+  for (int c = 0; c < kHostChunksMax; ++c)
+    if (s->host_streams[c]) cudaStreamDestroy(s->host_streams[c]);
   orca::grid_free(s->grid);
   delete s;
   return ORCA_OK;
@@ -521,13 +527,22 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
   DeviceGuard guard(s->device);
   int rc = ensure_host_staging(s);
   if (rc != ORCA_OK) return rc;
-  const size_t bytes = (size_t)s->E * s->N * sizeof(float2);
-  cudaStream_t st = s->host_stream;
-  if (upload_state) {
-    CUDA_TRY(cudaMemcpyAsync(s->d_pos, pos_host, bytes, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(s->d_vel, vel_host, bytes, cudaMemcpyHostToDevice, st));
+  // Envs are independent, so the batch is cut into contiguous env chunks, each on its own
+  // stream: upload -> step(s) -> download.  Chunk c's kernel runs while chunk c+1 uploads and
+  // chunk c-1 downloads (the two copy engines and the SMs all busy); the call costs about the
+  // slowest of the three stages instead of their sum.  The uniform-grid path (one huge env)
+  // cannot be cut and goes through as a single chunk.
+  const bool tile_path = s->N < s->grid_min_agents;
+  int chunks = 1;
+  if (tile_path) {
+    const long long agents = (long long)s->E * s->N;
+    chunks = (int)std::min<long long>(kHostChunksMax, std::max<long long>(1, agents / kHostChunkAgents));
+    if (const char* e = std::getenv("ORCA_B200_HOST_CHUNKS")) {  // dev knob
+      const int v = std::atoi(e);
+      if (v >= 1 && v <= kHostChunksMax) chunks = v;
+    }
+    chunks = std::min(chunks, s->E);
   }
-  CUDA_TRY(cudaMemcpyAsync(s->d_aux, pref_or_goal_host, bytes, cudaMemcpyHostToDevice, st));
   orca::StepArgs a;
   fill_common(s, &a);
   a.pos = s->d_pos;
@@ -536,13 +551,27 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
     a.pref = s->d_aux;
   else
     a.goal = s->d_aux;
-  for (int t = 0; t < steps; ++t) {
-    rc = launch_step(s, a, policy, st);
-    if (rc != ORCA_OK) return rc;
+  for (int c = 0; c < chunks; ++c) {
+    const int e0 = (int)((long long)s->E * c / chunks), e1 = (int)((long long)s->E * (c + 1) / chunks);
+    const size_t off = (size_t)e0 * s->N;  // in agents (= float2 elements = 2 floats)
+    const size_t bytes = (size_t)(e1 - e0) * s->N * sizeof(float2);
+    cudaStream_t st = s->host_streams[c];
+    if (upload_state) {
+      CUDA_TRY(cudaMemcpyAsync(s->d_pos + off, pos_host + 2 * off, bytes, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(s->d_vel + off, vel_host + 2 * off, bytes, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->d_aux + off, pref_or_goal_host + 2 * off, bytes, cudaMemcpyHostToDevice, st));
+    orca::StepArgs ac = a;
+    ac.env_base = e0;
+    ac.E = e1;
+    for (int t = 0; t < steps; ++t) {
+      rc = launch_step(s, ac, policy, st);
+      if (rc != ORCA_OK) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(pos_host + 2 * off, s->d_pos + off, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(vel_host + 2 * off, s->d_vel + off, bytes, cudaMemcpyDeviceToHost, st));
   }
-  CUDA_TRY(cudaMemcpyAsync(pos_host, s->d_pos, bytes, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(vel_host, s->d_vel, bytes, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int c = 0; c < chunks; ++c) CUDA_TRY(cudaStreamSynchronize(s->host_streams[c]));
   return ORCA_OK;
 }
 

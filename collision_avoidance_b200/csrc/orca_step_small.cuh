@@ -35,8 +35,8 @@ enum : int {
 };
 
 struct StepArgs {
-  // shape
-  int E, N, envs_per_block;
+  // shape: the launch covers envs [env_base, E)
+  int E, N, envs_per_block, env_base;
   // simulator parameters (uniform over the batch)
   int k;
   float dt, inv_dt, nd_sq, inv_th, inv_tho, radius, vmax, obst_range_sq;
@@ -96,8 +96,47 @@ struct TileSource {
   const float2* env_vel;
   int n;
   int self;
+  // Worlds of at most 16 agents: rank every candidate by counting instead of inserting into a
+  // sorted list.  rank(j) = number of candidates that go in front of j in (distSq, id) order;
+  // the accepted neighbors are the in-range candidates of rank < k, already in RVO2's order
+  // (stable insertion in ascending-id visiting order gives exactly this permutation, and the
+  // "range shrinks to the k-th best" rule rejects exactly the candidates of rank >= k).
+  // 120 independent compare/increment pairs with every lane live, against ~60 instructions
+  // per candidate under a divergent branch for the insertion.
+  template <class NK>
+  ORCA_HD void gather_ranked16(NK& nk, float2 p) const {
+    float d[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 q = env_pos[j < n ? j : 0];
+      // candidates that do not exist (j >= n) and the agent itself sit at distance +inf; adding
+      // the pad (instead of selecting) keeps the shared-memory load unconditional
+      const float pad = (j < n && j != self) ? 0.f : INFINITY;
+      d[j] = abs_sq(sub(p, q)) + pad;
+    }
+    int r[16];
+    rank16(d, r);
+    // sorted ids as nibbles: slot s of the list at bits [4 s, 4 s + 4) of (hi : lo)
+    unsigned lo = 0u, hi = 0u;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const bool in = d[j] < nk.range_sq && r[j] < nk.k;
+      cnt += in ? 1 : 0;
+      const unsigned bit = in ? ((unsigned)j << ((r[j] & 7) * 4)) : 0u;
+      lo |= (r[j] < 8) ? bit : 0u;
+      hi |= (r[j] < 8) ? 0u : bit;
+    }
+    nk.set_sorted_ids16(lo, hi, cnt);
+  }
   template <class NK>
   ORCA_HD void gather(NK& nk, float2 p, const Lines& scratch, int scratch_slots, unsigned mask) const {
+#ifndef ORCA_NO_RANKED16  // A/B switch: -DORCA_NO_RANKED16 builds the insertion path for small worlds too
+    if (n <= 16) {
+      gather_ranked16(nk, p);
+      return;
+    }
+#endif
     if (n <= 32) {
       // few candidates, most of them accepted by most lanes: insert directly
       for (int j = 0; j < n; ++j) {
@@ -259,7 +298,8 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
     for (int s = 0; s < K; ++s) {
       if (s < a.k) {
         a.nbr_idx[(size_t)g * a.k + s] = (nk.id[s] >= 0) ? src.local_id(nk.id[s]) : -1;
-        if (a.nbr_dsq != nullptr) a.nbr_dsq[(size_t)g * a.k + s] = (nk.id[s] >= 0) ? nk.d[s] : 0.f;
+        // recomputed with the expression of the search (same bits): the ranked path keeps no distances
+        if (a.nbr_dsq != nullptr) a.nbr_dsq[(size_t)g * a.k + s] = (nk.id[s] >= 0) ? abs_sq(sub(p, src.pos(nk.id[s]))) : 0.f;
         cnt += (nk.id[s] >= 0) ? 1 : 0;
       }
     }
@@ -435,7 +475,15 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
     offset += (w < warp) ? cw : 0;
     total += cw;
   }
-  if (need) s_queue[offset + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)tid;
+  // queue of the agents that need LP3 from the front of s_queue; from its back, the list of the
+  // columns of s_lines whose owner does NOT need LP3 (their lines are dead after LP2)
+  {
+    const unsigned below = (1u << lane) - 1u;
+    if (need)
+      s_queue[offset + __popc(bal & below)] = (unsigned short)tid;
+    else
+      s_queue[blockDim.x - 1 - ((warp << 5) - offset + __popc(~bal & below))] = (unsigned short)tid;
+  }
   __syncthreads();
 #if ORCA_LP3_SMEM_POOL
   // projected lines in a shared-memory pool of blockDim/2 entries (SoA, stride = pool size);
@@ -460,6 +508,13 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
   }
 #else
   (void)s_pool;
+  // Each solver thread borrows one dead column to keep the projected programme of its current
+  // LP3 round (computed once per round instead of once per access).  When more than half of the
+  // block needs LP3 there are not enough dead columns: the warps beyond them recompute the
+  // projections on access (lp3) -- same arithmetic, same result.
+  const int nfree = blockDim.x - total;
+  int nstored = total < nfree ? total : nfree;
+  if (nstored < total) nstored &= ~31;  // whole warps only: the LPs vote warp-wide
   if ((warp << 5) < total) {  // warp-uniform: this warp owns queue entries
     const bool mine = tid < total;
     const int owner = mine ? (int)s_queue[tid] : tid;
@@ -468,7 +523,14 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
     L.base = s_lines + owner;
     L.stride = blockDim.x;
     float2 nv = s_nv[owner];
-    lp3(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, nv);
+    if ((warp << 5) < nstored) {
+      Lines P;
+      P.base = s_lines + (mine ? (int)s_queue[blockDim.x - 1 - tid] : tid);
+      P.stride = blockDim.x;
+      lp3_stored(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, P, nv);
+    } else {
+      lp3(0xffffffffu, mine, L, meta & 0xff, (meta >> 8) & 0xff, (meta >> 16) & 0xff, vmax, nv);
+    }
     if (mine) s_nv[owner] = nv;
   }
 #endif
@@ -496,7 +558,8 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   const int N = a.N;
   const int le = tid / N;
   const int la = tid - le * N;
-  const int env = blockIdx.x * a.envs_per_block + le;
+  const int env0 = a.env_base + blockIdx.x * a.envs_per_block;  // first env of this block
+  const int env = env0 + le;
   const bool valid = (le < a.envs_per_block) && (env < a.E);
   const int g = env * N + la;
 
@@ -518,7 +581,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   // copies the ones of its envs into shared memory first.
   const int slots = a.world_slots;
   if (slots > 0) {
-    const size_t first = (size_t)blockIdx.x * a.envs_per_block * a.vert_stride;  // 0 for a shared world
+    const size_t first = (size_t)env0 * a.vert_stride;  // 0 for a shared world
     const size_t limit = (a.vert_stride > 0) ? (size_t)a.E * a.vert_stride : (size_t)a.world_verts;
     for (int s = tid; s < slots; s += tpb) {
       if (first + s < limit) {

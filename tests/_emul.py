@@ -19,7 +19,7 @@ c_f, c_i, c_p = ctypes.c_float, ctypes.c_int, ctypes.c_void_p
 class StepArgs(ctypes.Structure):
     """Mirror of orca::StepArgs (csrc/orca_step_small.cuh)."""
     _fields_ = [
-        ("E", c_i), ("N", c_i), ("envs_per_block", c_i), ("k", c_i),
+        ("E", c_i), ("N", c_i), ("envs_per_block", c_i), ("env_base", c_i), ("k", c_i),
         ("dt", c_f), ("inv_dt", c_f), ("nd_sq", c_f), ("inv_th", c_f), ("inv_tho", c_f), ("radius", c_f),
         ("vmax", c_f), ("obst_range_sq", c_f),
         ("pos", c_p), ("vel", c_p), ("pref", c_p), ("goal", c_p), ("goal2", c_p),

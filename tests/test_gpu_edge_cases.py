@@ -51,6 +51,17 @@ def test_generic_max_neighbors(k, nd):
     _one_step_vs_oracle(scn, steps=10)
 
 
+@pytest.mark.parametrize("N", [2, 10, 13, 16])
+@pytest.mark.parametrize("k", [1, 3, 5, 7, 10, 16])
+def test_ranked_selection_small_worlds(N, k):
+    """Worlds of <= 16 agents pick their neighbors by rank counting (TileSource::gather_ranked16),
+    not by sorted insertion: dense little crowds where more agents are in range than k allows."""
+    from collision_avoidance_b200 import scenarios
+    scn = scenarios.crowd(6, N, seed=100 * N + k)
+    scn.params = dict(scn.params, maxNeighbors=k, neighborDist=5.0)
+    _one_step_vs_oracle(scn, steps=6)
+
+
 def test_no_obstacles_and_per_env_obstacles():
     from collision_avoidance_b200 import scenarios
     scn = scenarios.crowd(4, 30, seed=60)
@@ -134,3 +145,32 @@ def test_host_buffer_entry_point_matches_device_path():
         b.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
     assert np.array_equal(a.pos.cpu().numpy(), pos_h.numpy().reshape(64, 16, 2))
     assert np.array_equal(a.vel.cpu().numpy(), vel_h.numpy().reshape(64, 16, 2))
+
+
+@pytest.mark.parametrize("chunks", [2, 5, 16])
+@pytest.mark.parametrize("world", ["circle", "crowd_blocks"])
+def test_host_entry_point_pipelined_chunks_equal_single_launch(monkeypatch, chunks, world):
+    """orca_step_host cuts the batch into env chunks on separate streams (upload | step | download
+    overlapped); every chunking must give the state of the unchunked device path, also with
+    per-env obstacle tables and a ragged env count."""
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    if world == "circle":
+        scn = scenarios.circle(67, 16, seed=81)
+    else:
+        scn = scenarios.crowd(13, 40, seed=82, blocks=4)   # per-env obstacle worlds
+    E, N = scn.num_envs, scn.agents_per_env
+    a, b = _mk(scn), _mk(scn)
+    goal = torch.from_numpy(scn.goal).cuda()
+    pos_h = torch.from_numpy(scn.pos.copy()).pin_memory()
+    vel_h = torch.from_numpy(scn.vel.copy()).pin_memory()
+    goal_h = torch.from_numpy(scn.goal.copy()).pin_memory()
+    monkeypatch.setenv("ORCA_B200_HOST_CHUNKS", str(chunks))
+    b.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=3)
+    for _ in range(3):
+        a.env_step(policy=_lib.POLICY_GOAL, goal=goal)
+    for _ in range(10):
+        a.env_step(policy=_lib.POLICY_GOAL, goal=goal)
+        b.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
+    assert np.array_equal(a.pos.cpu().numpy(), pos_h.numpy().reshape(E, N, 2))
+    assert np.array_equal(a.vel.cpu().numpy(), vel_h.numpy().reshape(E, N, 2))

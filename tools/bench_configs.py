@@ -81,7 +81,7 @@ def main():
     if "env" in which:
         E, N = 100_000, 10
         env = envs.Collision_Avoidance_Env(numAgents=N, num_envs=E, seed=4)
-        theta = (torch.rand(E, N, device="cuda") - 0.5) * 0.6
+        theta = (torch.rand(E, N, device="cuda", generator=torch.Generator("cuda").manual_seed(5)) - 0.5) * 0.6
         report("gym env 10 agents x100000 RL step + obs", E * N, timed(lambda: env.step(theta), steps, warmup), 45 + 256,
                env.sim.read_stats())
 
