@@ -333,7 +333,7 @@ def run_ours(args):
                          "note": "kernel is FP32-issue bound, not HBM bound; see DESIGN.md Roofline"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_state,
                     "d2h_bytes_per_step": 2 * bytes_state, "steps": e2e_steps,
-                    "api": "BatchedRVOSimulator.step_host -> orca_step_host (pinned host buffers; env chunks pipelined over streams: upload | step | download)"},
+                    "api": "BatchedRVOSimulator.step_host -> orca_step_host (pinned host buffers, mapped: the step kernel reads goals from and writes pos/vel to host memory over PCIe)"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "wall_s_timed_region": wall,

@@ -57,9 +57,21 @@ struct DeviceGuard {
 
 }  // namespace
 
-// orca_step_host pipelining: at most this many env chunks, of about this many agents each
+// orca_step_host pipelining: at most this many env chunks; batches below kHostChunkAgents are not cut
 constexpr int kHostChunksMax = 16;
-constexpr long long kHostChunkAgents = 131072;
+constexpr long long kHostChunkAgents = 65536;
+
+// what a captured orca_step_host graph depends on
+struct HostGraphKey {
+  const void* pos;
+  const void* vel;
+  const void* aux;
+  int policy, upload_state, steps, chunks;
+  bool operator==(const HostGraphKey& o) const {
+    return pos == o.pos && vel == o.vel && aux == o.aux && policy == o.policy && upload_state == o.upload_state &&
+           steps == o.steps && chunks == o.chunks;
+  }
+};
 
 struct OrcaSim {
   OrcaParams p{};
@@ -81,6 +93,11 @@ struct OrcaSim {
   float2* d_vel = nullptr;
   float2* d_aux = nullptr;
   cudaStream_t host_streams[kHostChunksMax] = {};
+  cudaEvent_t host_fork = nullptr;
+  cudaEvent_t host_join[kHostChunksMax] = {};
+  HostGraphKey host_graph_key{};
+  cudaGraphExec_t host_graph_exec = nullptr;  // the captured upload | step | download fan-out
+  int64_t host_graph_launches = 0;             // kernel launches one replay performs
   // uniform-grid scratch (large worlds)
   orca::GridScratch grid;
   int64_t launches = 0;
@@ -89,6 +106,10 @@ struct OrcaSim {
 namespace {
 
 void free_obstacles(OrcaSim* s) {
+  if (s->host_graph_exec) {  // the captured host step has the old tables baked into its kernel arguments
+    cudaGraphExecDestroy(s->host_graph_exec);
+    s->host_graph_exec = nullptr;
+  }
   cudaFree(s->d_vert_pd);
   cudaFree(s->d_vert_link);
   cudaFree(s->d_bsp);
@@ -198,7 +219,11 @@ int ensure_host_staging(OrcaSim* s) {
   CUDA_TRY(cudaMalloc(&s->d_pos, bytes));
   CUDA_TRY(cudaMalloc(&s->d_vel, bytes));
   CUDA_TRY(cudaMalloc(&s->d_aux, bytes));
-  for (int c = 0; c < kHostChunksMax; ++c) CUDA_TRY(cudaStreamCreateWithFlags(&s->host_streams[c], cudaStreamNonBlocking));
+  for (int c = 0; c < kHostChunksMax; ++c) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->host_streams[c], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->host_join[c], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&s->host_fork, cudaEventDisableTiming));
   return ORCA_OK;
 }
 
@@ -243,8 +268,12 @@ int orca_destroy(OrcaSim* s) {
   cudaFree(s->d_pos);
   cudaFree(s->d_vel);
   cudaFree(s->d_aux);
-  for (int c = 0; c < kHostChunksMax; ++c)
+  if (s->host_graph_exec) cudaGraphExecDestroy(s->host_graph_exec);
+  for (int c = 0; c < kHostChunksMax; ++c) {
     if (s->host_streams[c]) cudaStreamDestroy(s->host_streams[c]);
+    if (s->host_join[c]) cudaEventDestroy(s->host_join[c]);
+  }
+  if (s->host_fork) cudaEventDestroy(s->host_fork);
   orca::grid_free(s->grid);
   delete s;
   return ORCA_OK;
@@ -527,51 +556,163 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
   DeviceGuard guard(s->device);
   int rc = ensure_host_staging(s);
   if (rc != ORCA_OK) return rc;
+  // ---- direct path: the host buffers are pinned and mapped -------------------------------------
+  // The step kernel itself reads the goals / preferred velocities from the caller's buffer and
+  // writes the new positions and velocities into the caller's buffers (as well as into the
+  // device-resident state) over PCIe while it computes: no staging copies, no copy-engine
+  // start-up per chunk, the transfers overlap the arithmetic warp by warp.  One launch per step.
+  const bool tile_path = s->N < s->grid_min_agents;
+  if (tile_path && std::getenv("ORCA_B200_HOST_NO_MAPPED") == nullptr) {
+    void *m_pos = nullptr, *m_vel = nullptr, *m_aux = nullptr;
+    const bool mapped = cudaHostGetDevicePointer(&m_pos, pos_host, 0) == cudaSuccess &&
+                        cudaHostGetDevicePointer(&m_vel, vel_host, 0) == cudaSuccess &&
+                        cudaHostGetDevicePointer(&m_aux, const_cast<float*>(pref_or_goal_host), 0) == cudaSuccess;
+    if (!mapped) {
+      cudaGetLastError();  // pageable buffers: clear the error, take the staged path below
+    } else {
+      const size_t bytes = (size_t)s->E * s->N * sizeof(float2);
+      cudaStream_t st = s->host_streams[0];
+      if (upload_state) {
+        CUDA_TRY(cudaMemcpyAsync(s->d_pos, pos_host, bytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s->d_vel, vel_host, bytes, cudaMemcpyHostToDevice, st));
+      }
+      orca::StepArgs a;
+      fill_common(s, &a);
+      a.pos = s->d_pos;
+      a.vel = s->d_vel;
+      const float2* aux = static_cast<const float2*>(m_aux);
+      if (steps > 1) {  // read every step: bring it over once
+        CUDA_TRY(cudaMemcpyAsync(s->d_aux, pref_or_goal_host, bytes, cudaMemcpyHostToDevice, st));
+        aux = s->d_aux;
+      }
+      if (policy == ORCA_POLICY_EXTERNAL)
+        a.pref = aux;
+      else
+        a.goal = const_cast<float2*>(aux);
+      for (int t = 0; t < steps; ++t) {
+        if (t == steps - 1) {
+          a.pos_mirror = static_cast<float2*>(m_pos);
+          a.vel_mirror = static_cast<float2*>(m_vel);
+        }
+        rc = launch_step(s, a, policy, st);
+        if (rc != ORCA_OK) return rc;
+      }
+      CUDA_TRY(cudaStreamSynchronize(st));
+      return ORCA_OK;
+    }
+  }
+  // ---- staged path (pageable host buffers, or the uniform-grid pipeline) -----------------------
   // Envs are independent, so the batch is cut into contiguous env chunks, each on its own
   // stream: upload -> step(s) -> download.  Chunk c's kernel runs while chunk c+1 uploads and
   // chunk c-1 downloads (the two copy engines and the SMs all busy); the call costs about the
   // slowest of the three stages instead of their sum.  The uniform-grid path (one huge env)
   // cannot be cut and goes through as a single chunk.
-  const bool tile_path = s->N < s->grid_min_agents;
+  //
+  // The whole fan-out (4 calls per chunk) is captured once into a CUDA graph keyed by the
+  // buffers and arguments, and replayed with a single launch on later calls: issued call by
+  // call, the CPU cost of ~16-64 runtime calls was as long as the transfers themselves.
+  //
+  // Chunks are NOT equal: what the call cannot hide is the first chunk's upload + step (nothing
+  // to download yet) while the downloads want to be few and large (a 0.5 MB copy reaches 47 GB/s
+  // here, 4 MB 55 GB/s).  So the first chunk is small and the sizes grow: weights 1 : 3 : 6 : 6.
   int chunks = 1;
   if (tile_path) {
     const long long agents = (long long)s->E * s->N;
-    chunks = (int)std::min<long long>(kHostChunksMax, std::max<long long>(1, agents / kHostChunkAgents));
+    chunks = agents >= kHostChunkAgents * 4 ? 4 : (agents >= kHostChunkAgents ? 2 : 1);
     if (const char* e = std::getenv("ORCA_B200_HOST_CHUNKS")) {  // dev knob
       const int v = std::atoi(e);
       if (v >= 1 && v <= kHostChunksMax) chunks = v;
     }
     chunks = std::min(chunks, s->E);
   }
-  orca::StepArgs a;
-  fill_common(s, &a);
-  a.pos = s->d_pos;
-  a.vel = s->d_vel;
-  if (policy == ORCA_POLICY_EXTERNAL)
-    a.pref = s->d_aux;
-  else
-    a.goal = s->d_aux;
-  for (int c = 0; c < chunks; ++c) {
-    const int e0 = (int)((long long)s->E * c / chunks), e1 = (int)((long long)s->E * (c + 1) / chunks);
-    const size_t off = (size_t)e0 * s->N;  // in agents (= float2 elements = 2 floats)
-    const size_t bytes = (size_t)(e1 - e0) * s->N * sizeof(float2);
-    cudaStream_t st = s->host_streams[c];
-    if (upload_state) {
-      CUDA_TRY(cudaMemcpyAsync(s->d_pos + off, pos_host + 2 * off, bytes, cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(s->d_vel + off, vel_host + 2 * off, bytes, cudaMemcpyHostToDevice, st));
+  // env boundaries from cumulative weights 1, 3, 6, 6, 6, ...
+  int bound[kHostChunksMax + 1];
+  {
+    long long wsum = 0, acc = 0;
+    for (int c = 0; c < chunks; ++c) wsum += (c == 0 ? 1 : (c == 1 ? 3 : 6));
+    bound[0] = 0;
+    for (int c = 0; c < chunks; ++c) {
+      acc += (c == 0 ? 1 : (c == 1 ? 3 : 6));
+      bound[c + 1] = (int)((long long)s->E * acc / wsum);
     }
-    CUDA_TRY(cudaMemcpyAsync(s->d_aux + off, pref_or_goal_host + 2 * off, bytes, cudaMemcpyHostToDevice, st));
-    orca::StepArgs ac = a;
-    ac.env_base = e0;
-    ac.E = e1;
-    for (int t = 0; t < steps; ++t) {
-      rc = launch_step(s, ac, policy, st);
-      if (rc != ORCA_OK) return rc;
-    }
-    CUDA_TRY(cudaMemcpyAsync(pos_host + 2 * off, s->d_pos + off, bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(vel_host + 2 * off, s->d_vel + off, bytes, cudaMemcpyDeviceToHost, st));
+    for (int c = 1; c <= chunks; ++c) bound[c] = std::max(bound[c], std::min(s->E, bound[c - 1] + 1));  // no empty chunk
+    bound[chunks] = s->E;
   }
-  for (int c = 0; c < chunks; ++c) CUDA_TRY(cudaStreamSynchronize(s->host_streams[c]));
+  HostGraphKey key{pos_host, vel_host, pref_or_goal_host, policy, upload_state, steps, chunks};
+  const bool use_graph = tile_path && std::getenv("ORCA_B200_HOST_NO_GRAPH") == nullptr;
+  if (use_graph && s->host_graph_exec != nullptr && !(key == s->host_graph_key)) {
+    cudaGraphExecDestroy(s->host_graph_exec);
+    s->host_graph_exec = nullptr;
+  }
+  cudaStream_t root = s->host_streams[0];
+  if (!use_graph || s->host_graph_exec == nullptr) {
+    if (use_graph) {
+      CUDA_TRY(cudaStreamBeginCapture(root, cudaStreamCaptureModeThreadLocal));
+      CUDA_TRY(cudaEventRecord(s->host_fork, root));
+      for (int c = 1; c < chunks; ++c) CUDA_TRY(cudaStreamWaitEvent(s->host_streams[c], s->host_fork, 0));
+    }
+    orca::StepArgs a;
+    fill_common(s, &a);
+    a.pos = s->d_pos;
+    a.vel = s->d_vel;
+    if (policy == ORCA_POLICY_EXTERNAL)
+      a.pref = s->d_aux;
+    else
+      a.goal = s->d_aux;
+    const int64_t launches_before = s->launches;
+    rc = ORCA_OK;
+    cudaError_t ce = cudaSuccess;
+    for (int c = 0; c < chunks && rc == ORCA_OK && ce == cudaSuccess; ++c) {
+      const int e0 = bound[c], e1 = bound[c + 1];
+      const size_t off = (size_t)e0 * s->N;  // in agents (= float2 elements = 2 floats)
+      const size_t bytes = (size_t)(e1 - e0) * s->N * sizeof(float2);
+      cudaStream_t st = s->host_streams[c];
+      if (upload_state) {
+        ce = cudaMemcpyAsync(s->d_pos + off, pos_host + 2 * off, bytes, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(s->d_vel + off, vel_host + 2 * off, bytes, cudaMemcpyHostToDevice, st);
+      }
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(s->d_aux + off, pref_or_goal_host + 2 * off, bytes, cudaMemcpyHostToDevice, st);
+      orca::StepArgs ac = a;
+      ac.env_base = e0;
+      ac.E = e1;
+      for (int t = 0; t < steps && rc == ORCA_OK && ce == cudaSuccess; ++t) rc = launch_step(s, ac, policy, st);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(pos_host + 2 * off, s->d_pos + off, bytes, cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(vel_host + 2 * off, s->d_vel + off, bytes, cudaMemcpyDeviceToHost, st);
+      if (use_graph && c > 0 && ce == cudaSuccess) {
+        ce = cudaEventRecord(s->host_join[c], st);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(root, s->host_join[c], 0);
+      }
+    }
+    if (use_graph) {
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ee = cudaStreamEndCapture(root, &graph);  // always end the capture
+      if (rc != ORCA_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (ce != cudaSuccess || ee != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return fail(ORCA_ERR_CUDA, "capturing the host-step graph failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+      }
+      const cudaError_t ie = cudaGraphInstantiate(&s->host_graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        s->host_graph_exec = nullptr;
+        return fail(ORCA_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+      }
+      s->host_graph_key = key;
+      s->host_graph_launches = s->launches - launches_before;
+      s->launches = launches_before;  // nothing ran yet: capture only recorded the launches
+    } else {
+      if (rc != ORCA_OK) return rc;
+      if (ce != cudaSuccess) return fail(ORCA_ERR_CUDA, "host step failed: %s", cudaGetErrorString(ce));
+      for (int c = 0; c < chunks; ++c) CUDA_TRY(cudaStreamSynchronize(s->host_streams[c]));
+      return ORCA_OK;
+    }
+  }
+  CUDA_TRY(cudaGraphLaunch(s->host_graph_exec, root));
+  s->launches += s->host_graph_launches;
+  CUDA_TRY(cudaStreamSynchronize(root));
   return ORCA_OK;
 }
 

@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(128, 6) step_grid_kernel(const StepArgs a, con
   c.p = v2(0.f, 0.f);
   c.v = v2(0.f, 0.f);
   c.nv = v2(0.f, 0.f);
+  c.aim = v2(0.f, 0.f);
   c.n = c.n_obst = c.fail = 0;
   int g = 0, env = 0, la = 0, estep = 0;
   bool alive = valid;
@@ -363,6 +364,7 @@ __global__ void __launch_bounds__(128, 6) step_grid_kernel(const StepArgs a, con
     L.stride = tpb;
     c.p = spos[j];
     c.v = svel[j];
+    if (!a.neighbors_only) c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];
     alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid

@@ -87,6 +87,10 @@ struct StepArgs {
   // 1: uniform-grid path; an env spans several blocks, so its step counter is bumped by a
   // separate kernel instead of by the env's first agent
   int grid_path;
+  // optional second destination of the post-step state: the caller's host buffers mapped into
+  // the device address space (orca_step_host), written by the kernel itself over PCIe
+  float2* pos_mirror;
+  float2* vel_mirror;
 };
 
 // Where an agent's neighbor candidates come from.  TileSource: the pre-step snapshot of the
@@ -198,6 +202,8 @@ ORCA_HD void counter_inc(int* c) {
 // across the LP3 stage to the back half (integration, reward, bandit update, done test).
 struct AgentCarry {
   float2 p, v;     // pre-step state
+  float2 aim;      // the agent's input of the step, loaded by the caller as early as possible (it may
+                   // live in mapped host memory, a PCIe round trip away): goal, or pref when EXTERNAL
   float2 gdir;     // unit vector to the goal (pre-step position)
   float2 pref;     // preferred velocity handed to ORCA
   float2 nv;       // new velocity
@@ -234,9 +240,9 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
   int act = 0;
   float w_act[POLICY == POLICY_ALAN ? ORCA_MAX_ACTIONS : 1];
   if (POLICY == POLICY_EXTERNAL) {
-    pref = a.pref[g];
+    pref = c.aim;
   } else {
-    gdir = goal_direction(p, a.goal[g]);
+    gdir = goal_direction(p, c.aim);
     pref = gdir;
     if (POLICY == POLICY_RL) {
       float sn, cs;
@@ -351,6 +357,10 @@ ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const in
   const float2 p = add(c.p, mul(a.dt, v));  // position += velocity * timeStep
   a.pos[g] = p;
   a.vel[g] = v;
+  if (a.pos_mirror != nullptr) {
+    a.pos_mirror[g] = p;
+    a.vel_mirror[g] = v;
+  }
 
   // ---------------- reward / bandit update ----------------
   if (POLICY == POLICY_RL || POLICY == POLICY_ALAN) {
@@ -407,6 +417,7 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
   AgentCarry c;
   c.p = p;
   c.v = v;
+  c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];
   if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c)) return;
   lp3(warp_mask, c.fail < c.n, L, c.n, c.n_obst, c.fail, a.vmax, c.nv);
   agent_back<POLICY>(a, env, la, g, estep, c);
@@ -569,7 +580,9 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   c.nv = v2(0.f, 0.f);
   c.n = c.n_obst = c.fail = 0;
   int estep = 0;
+  c.aim = v2(0.f, 0.f);
   if (valid) {
+    if (!a.neighbors_only) c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];  // consumed after the barrier
     c.p = a.pos[g];
     c.v = a.vel[g];
     s_pos[tid] = c.p;

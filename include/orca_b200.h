@@ -188,8 +188,15 @@ int orca_observe(OrcaSim* sim, const float* pos_dev, const float* vel_dev, const
                  const int32_t* obst_nbr_cnt_dev, int laser_num, int circle_approx_num, float* obs_dev, void* stream);
 
 /* Host-buffer variant of orca_step (the e2e path: what a PyRVOSimulator-style caller
- * pays): copies pref (and, if `upload_state`, pos/vel) host->device, steps `steps` times
- * with the given policy, copies pos/vel back, synchronises.  Buffers should be pinned. */
+ * pays): takes pref / goal (and, if `upload_state`, pos/vel) from host buffers, steps `steps`
+ * times with the given policy (EXTERNAL or GOAL), leaves the new pos/vel in the host buffers,
+ * synchronises.  Two routes, same results:
+ *   - pinned (cudaHostAlloc / cudaHostRegister, i.e. mapped) buffers: the step kernel reads the
+ *     input from and writes the new state into the caller's buffers itself, over PCIe, while it
+ *     computes -- one launch, no staging copies;
+ *   - pageable buffers, or the uniform-grid pipeline: staged copies, the batch cut into env
+ *     chunks on separate streams (upload | step | download overlapped), replayed from a CUDA
+ *     graph while the arguments stay the same. */
 int orca_step_host(OrcaSim* sim, float* pos_host, float* vel_host, const float* pref_or_goal_host, int policy,
                    int upload_state, int steps);
 

@@ -33,6 +33,7 @@ class StepArgs(ctypes.Structure):
         ("stats", c_p),
         ("vert_pd", c_p), ("vert_link", c_p), ("bsp", c_p), ("bsp_seg", c_p), ("env_nodes", c_p),
         ("shared_nodes", c_i), ("vert_stride", c_i), ("world_slots", c_i), ("world_verts", c_i), ("neighbors_only", c_i), ("grid_path", c_i),
+        ("pos_mirror", c_p), ("vel_mirror", c_p),
     ]
 
 

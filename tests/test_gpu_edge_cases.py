@@ -147,12 +147,16 @@ def test_host_buffer_entry_point_matches_device_path():
     assert np.array_equal(a.vel.cpu().numpy(), vel_h.numpy().reshape(64, 16, 2))
 
 
+@pytest.mark.parametrize("mode", ["mapped", "pageable", "staged_graph", "staged_calls"])
 @pytest.mark.parametrize("chunks", [2, 5, 16])
 @pytest.mark.parametrize("world", ["circle", "crowd_blocks"])
-def test_host_entry_point_pipelined_chunks_equal_single_launch(monkeypatch, chunks, world):
-    """orca_step_host cuts the batch into env chunks on separate streams (upload | step | download
-    overlapped); every chunking must give the state of the unchunked device path, also with
-    per-env obstacle tables and a ragged env count."""
+def test_host_entry_point_pipelined_chunks_equal_single_launch(monkeypatch, chunks, world, mode):
+    """orca_step_host has two routes.  Pinned (mapped) host buffers: the kernel reads the goals
+    from and writes the new state into the caller's buffers itself.  Otherwise (pageable buffers, or
+    ORCA_B200_HOST_NO_MAPPED): the batch is cut into env chunks on separate streams (upload | step |
+    download overlapped), replayed from a CUDA graph or issued call by call.  Every route and every
+    chunking must give the state of the plain device path, also with per-env obstacle tables and
+    a ragged env count."""
     import torch
     from collision_avoidance_b200 import _lib, scenarios
     if world == "circle":
@@ -162,10 +166,14 @@ def test_host_entry_point_pipelined_chunks_equal_single_launch(monkeypatch, chun
     E, N = scn.num_envs, scn.agents_per_env
     a, b = _mk(scn), _mk(scn)
     goal = torch.from_numpy(scn.goal).cuda()
-    pos_h = torch.from_numpy(scn.pos.copy()).pin_memory()
-    vel_h = torch.from_numpy(scn.vel.copy()).pin_memory()
-    goal_h = torch.from_numpy(scn.goal.copy()).pin_memory()
+    pos_h, vel_h, goal_h = (torch.from_numpy(x.copy()) for x in (scn.pos, scn.vel, scn.goal))
+    if mode != "pageable":
+        pos_h, vel_h, goal_h = pos_h.pin_memory(), vel_h.pin_memory(), goal_h.pin_memory()
     monkeypatch.setenv("ORCA_B200_HOST_CHUNKS", str(chunks))
+    if mode.startswith("staged"):
+        monkeypatch.setenv("ORCA_B200_HOST_NO_MAPPED", "1")
+    if mode == "staged_calls":
+        monkeypatch.setenv("ORCA_B200_HOST_NO_GRAPH", "1")   # call-by-call issue instead of graph replay
     b.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=3)
     for _ in range(3):
         a.env_step(policy=_lib.POLICY_GOAL, goal=goal)
@@ -174,3 +182,9 @@ def test_host_entry_point_pipelined_chunks_equal_single_launch(monkeypatch, chun
         b.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
     assert np.array_equal(a.pos.cpu().numpy(), pos_h.numpy().reshape(E, N, 2))
     assert np.array_equal(a.vel.cpu().numpy(), vel_h.numpy().reshape(E, N, 2))
+    # new obstacles invalidate the captured graph (its kernels carry the old table pointers)
+    b.set_obstacles([], per_env=False)
+    a.set_obstacles([], per_env=False)
+    a.env_step(policy=_lib.POLICY_GOAL, goal=goal)
+    b.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
+    assert np.array_equal(a.pos.cpu().numpy(), pos_h.numpy().reshape(E, N, 2))
