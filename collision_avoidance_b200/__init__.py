@@ -18,7 +18,7 @@ def __getattr__(name):
     if name == "BatchedRVOSimulator":
         from .sim import BatchedRVOSimulator
         return BatchedRVOSimulator
-    if name in ("scenarios", "sim", "rvo2_compat", "envs", "alan", "actfile", "dist"):
+    if name in ("scenarios", "sim", "rvo2_compat", "envs", "alan", "actfile", "dist", "mcmc", "policy"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)

@@ -20,6 +20,7 @@
 #include "orca_core.cuh"
 #include "orca_grid.cuh"
 #include "orca_obs.cuh"
+#include "orca_policy.cuh"
 #include "orca_step_small.cuh"
 
 namespace {
@@ -713,6 +714,49 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
   CUDA_TRY(cudaGraphLaunch(s->host_graph_exec, root));
   s->launches += s->host_graph_launches;
   CUDA_TRY(cudaStreamSynchronize(root));
+  return ORCA_OK;
+}
+
+int orca_policy_mlp(OrcaSim* s, const float* obs_dev, int64_t rows, const OrcaMlpWeights* w, float* out_dev, void* stream) {
+  if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (w == nullptr || obs_dev == nullptr || out_dev == nullptr) return fail(ORCA_ERR_INVALID, "orca_policy_mlp: null pointer argument");
+  if (w->struct_size != sizeof(OrcaMlpWeights)) return fail(ORCA_ERR_INVALID, "OrcaMlpWeights.struct_size mismatch");
+  if (w->w1_dev == nullptr || w->b1_dev == nullptr || w->w2_dev == nullptr || w->b2_dev == nullptr || w->w3_dev == nullptr ||
+      w->b3_dev == nullptr)
+    return fail(ORCA_ERR_INVALID, "orca_policy_mlp: null weight pointer");
+  if (w->in_dim != orca::kMlpIn || w->hidden_dim != orca::kMlpHidden)
+    return fail(ORCA_ERR_UNSUPPORTED, "policy network must be %d -> %d -> %d -> out (got in=%d hidden=%d)", orca::kMlpIn,
+                orca::kMlpHidden, orca::kMlpHidden, w->in_dim, w->hidden_dim);
+  if (w->out_dim < 1 || w->out_dim > orca::kMlpMaxOut)
+    return fail(ORCA_ERR_UNSUPPORTED, "policy outputs must be in [1, %d]", orca::kMlpMaxOut);
+  if (rows < 0) return fail(ORCA_ERR_INVALID, "rows must be >= 0");
+  if (rows == 0) return ORCA_OK;
+  if ((reinterpret_cast<uintptr_t>(obs_dev) | reinterpret_cast<uintptr_t>(w->w1_dev) | reinterpret_cast<uintptr_t>(w->w2_dev)) & 15)
+    return fail(ORCA_ERR_INVALID, "obs_dev, w1_dev and w2_dev must be 16-byte aligned");
+  DeviceGuard guard(s->device);
+  orca::MlpArgs a;
+  a.obs = obs_dev;
+  a.rows = rows;
+  a.w1 = w->w1_dev;
+  a.b1 = w->b1_dev;
+  a.w2 = w->w2_dev;
+  a.b2 = w->b2_dev;
+  a.w3 = w->w3_dev;
+  a.b3 = w->b3_dev;
+  a.n_out = w->out_dim;
+  a.out = out_dev;
+  static bool attr_set = false;
+  static int sm_count = 0;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(orca::policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::mlp_smem_bytes()));
+    CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, s->device));
+    attr_set = true;
+  }
+  const long long tiles = (rows + orca::kMlpTile - 1) / orca::kMlpTile;
+  const int blocks = (int)std::min<long long>(tiles, 2ll * sm_count);  // persistent: 2 resident blocks per SM
+  orca::policy_mlp_kernel<<<blocks, orca::kMlpThreads, orca::mlp_smem_bytes(), static_cast<cudaStream_t>(stream)>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  s->launches += 1;
   return ORCA_OK;
 }
 

@@ -412,22 +412,24 @@ ORCA_HD float4 agent_line(float2 p, float2 v, float2 po, float2 vo, float cr, fl
   return out;
 }
 
-// ---- ranks of 16 keys -------------------------------------------------------------------------------
+// ---- ranks of M keys --------------------------------------------------------------------------------
 // r[j] = number of keys that sort in front of key j in (value, index) order: the stable sorting
-// permutation by counting.  All 120 pair comparisons are independent of each other.
+// permutation by counting.  All M (M - 1) / 2 pair comparisons are independent of each other.
 // Device version: one FSET per pair yields 1.0f or 0.0f; its BIT PATTERN (0x3f800000 = 127 * 2^23)
 // is accumulated with integer adds, two addends per IADD3, so a pair costs 2 instructions
 // instead of compare + select + 2 adds.  The sum wraps mod 2^32, i.e. (count * 127 mod 512) sits
-// in bits 23..31; 127 is invertible mod 512 (127 * 383 = 95 * 512 + 1), which recovers the count.
-ORCA_HD void rank16(const float* d, int* r) {
+// in bits 23..31; 127 is invertible mod 512 (127 * 383 = 95 * 512 + 1), which recovers any
+// count below 512.
+template <int M>
+ORCA_HD void rank_count(const float* d, int* r) {
 #if defined(__CUDA_ARCH__)
-  unsigned u[16];
+  unsigned u[M];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) u[j] = (unsigned)j * 0x3f800000u;
+  for (int j = 0; j < M; ++j) u[j] = (unsigned)j * 0x3f800000u;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < M; ++i) {
 #pragma unroll
-    for (int j = i + 1; j < 16; ++j) {
+    for (int j = i + 1; j < M; ++j) {
       float j_first;  // 1.0f when key j goes in front of key i (equal values: the lower index stays in front)
       asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(j_first) : "f"(d[j]), "f"(d[i]));
       u[i] += __float_as_uint(j_first);
@@ -435,11 +437,11 @@ ORCA_HD void rank16(const float* d, int* r) {
     }
   }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) r[j] = (int)(((u[j] >> 23) * 383u) & 511u);
+  for (int j = 0; j < M; ++j) r[j] = (int)(((u[j] >> 23) * 383u) & 511u);
 #else
-  for (int j = 0; j < 16; ++j) r[j] = j;
-  for (int i = 0; i < 16; ++i) {
-    for (int j = i + 1; j < 16; ++j) {
+  for (int j = 0; j < M; ++j) r[j] = j;
+  for (int i = 0; i < M; ++i) {
+    for (int j = i + 1; j < M; ++j) {
       const int j_first = (d[j] < d[i]) ? 1 : 0;
       r[i] += j_first;
       r[j] -= j_first;
@@ -470,13 +472,13 @@ struct NearestK {
       id[s] = -1;
     }
   }
-  // The list handed over ready-made by a caller that ranked its candidates itself (at most 16 of
-  // them): ids of slots 0..cnt-1 as nibbles of (hi : lo).  Distances are not kept.
-  ORCA_HD void set_sorted_ids16(unsigned lo, unsigned hi, int cnt) {
+  // The list handed over ready-made by a caller that ranked its candidates itself: the id of slot
+  // s in byte s of `packed` (16 bytes), slots 0..cnt-1 valid.  Distances are not kept.
+  ORCA_HD void set_sorted_ids(const uint4 packed, int cnt) {
 #pragma unroll
     for (int s = 0; s < K; ++s) {
-      const unsigned w = (s < 8) ? lo : hi;
-      id[s] = (s < cnt) ? (int)((w >> ((s & 7) * 4)) & 15u) : -1;
+      const unsigned w = (s < 4) ? packed.x : (s < 8) ? packed.y : (s < 12) ? packed.z : packed.w;
+      id[s] = (s < cnt) ? (int)((w >> ((s & 3) * 8)) & 255u) : -1;
       d[s] = 0.f;
     }
   }

@@ -100,44 +100,47 @@ struct TileSource {
   const float2* env_vel;
   int n;
   int self;
-  // Worlds of at most 16 agents: rank every candidate by counting instead of inserting into a
+  // Worlds of at most 32 agents: rank every candidate by counting instead of inserting into a
   // sorted list.  rank(j) = number of candidates that go in front of j in (distSq, id) order;
   // the accepted neighbors are the in-range candidates of rank < k, already in RVO2's order
   // (stable insertion in ascending-id visiting order gives exactly this permutation, and the
   // "range shrinks to the k-th best" rule rejects exactly the candidates of rank >= k).
-  // 120 independent compare/increment pairs with every lane live, against ~60 instructions
-  // per candidate under a divergent branch for the insertion.
-  template <class NK>
-  ORCA_HD void gather_ranked16(NK& nk, float2 p) const {
-    float d[16];
+  // M (M - 1) / 2 independent compare/accumulate pairs with every lane live, against ~80
+  // instructions per candidate under a divergent branch for the insertion.
+  // The sorted ids are scattered as bytes into the agent's first line slot (not in use yet) and
+  // read back with one 16-byte load.
+  template <int M, class NK>
+  ORCA_HD void gather_ranked(NK& nk, float2 p, const Lines& scratch) const {
+    float d[M];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < M; ++j) {
       const float2 q = env_pos[j < n ? j : 0];
       // candidates that do not exist (j >= n) and the agent itself sit at distance +inf; adding
       // the pad (instead of selecting) keeps the shared-memory load unconditional
       const float pad = (j < n && j != self) ? 0.f : INFINITY;
       d[j] = abs_sq(sub(p, q)) + pad;
     }
-    int r[16];
-    rank16(d, r);
-    // sorted ids as nibbles: slot s of the list at bits [4 s, 4 s + 4) of (hi : lo)
-    unsigned lo = 0u, hi = 0u;
+    int r[M];
+    rank_count<M>(d, r);
+    unsigned char* slot = reinterpret_cast<unsigned char*>(scratch.base);
     int cnt = 0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const bool in = d[j] < nk.range_sq && r[j] < nk.k;
+    for (int j = 0; j < M; ++j) {
+      const bool in = d[j] < nk.range_sq && r[j] < nk.k;  // k <= 16: the rank fits the 16-byte slot
       cnt += in ? 1 : 0;
-      const unsigned bit = in ? ((unsigned)j << ((r[j] & 7) * 4)) : 0u;
-      lo |= (r[j] < 8) ? bit : 0u;
-      hi |= (r[j] < 8) ? 0u : bit;
+      if (in) slot[r[j]] = (unsigned char)j;
     }
-    nk.set_sorted_ids16(lo, hi, cnt);
+    nk.set_sorted_ids(*reinterpret_cast<const uint4*>(scratch.base), cnt);
   }
   template <class NK>
   ORCA_HD void gather(NK& nk, float2 p, const Lines& scratch, int scratch_slots, unsigned mask) const {
 #ifndef ORCA_NO_RANKED16  // A/B switch: -DORCA_NO_RANKED16 builds the insertion path for small worlds too
     if (n <= 16) {
-      gather_ranked16(nk, p);
+      gather_ranked<16>(nk, p, scratch);
+      return;
+    }
+    if (n <= 32) {
+      gather_ranked<32>(nk, p, scratch);
       return;
     }
 #endif

@@ -187,6 +187,29 @@ int orca_observe(OrcaSim* sim, const float* pos_dev, const float* vel_dev, const
                  const int32_t* nbr_idx_dev, const int32_t* nbr_cnt_dev, const int32_t* obst_nbr_idx_dev,
                  const int32_t* obst_nbr_cnt_dev, int laser_num, int circle_approx_num, float* obs_dev, void* stream);
 
+/* Weights of the shared policy network (run_rllib.py:35-52, CustomModel1: fc1 64->64 ReLU,
+ * fc2 64->64 ReLU, fc_out 64->out_dim linear).  Matrices are [in][out] row-major (the layout of
+ * slim.fully_connected's `weights`), float32, device pointers; w1_dev and w2_dev 16-byte aligned. */
+typedef struct OrcaMlpWeights {
+  uint32_t struct_size; /* = sizeof(OrcaMlpWeights) */
+  int32_t in_dim;       /* 64: laser_num(16) * 4 */
+  int32_t hidden_dim;   /* 64 */
+  int32_t out_dim;      /* 1..8 (PPO on the env's Box(1) action space: mean, log-std) */
+  const float* w1_dev;
+  const float* b1_dev;
+  const float* w2_dev;
+  const float* b2_dev;
+  const float* w3_dev;
+  const float* b3_dev;
+} OrcaMlpWeights;
+
+/* Forward pass of that network for `rows` observation rows ([rows][64], e.g. the buffer
+ * orca_observe wrote for E*N agents): out_dev[rows][out_dim].  Replaces the per-env TensorFlow
+ * evaluation inside RLlib's rollout workers (run_rllib.py:35-52,96-112) so that
+ * observe -> policy -> orca_env_step stays on the device.  Asynchronous on `stream`. */
+int orca_policy_mlp(OrcaSim* sim, const float* obs_dev, int64_t rows, const OrcaMlpWeights* weights, float* out_dev,
+                    void* stream);
+
 /* Host-buffer variant of orca_step (the e2e path: what a PyRVOSimulator-style caller
  * pays): takes pref / goal (and, if `upload_state`, pos/vel) from host buffers, steps `steps`
  * times with the given policy (EXTERNAL or GOAL), leaves the new pos/vel in the host buffers,

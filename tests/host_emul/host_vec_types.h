@@ -3,4 +3,7 @@
 #pragma once
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct uint4 {
+  unsigned x, y, z, w;
+};
 struct int4 { int x, y, z, w; };
