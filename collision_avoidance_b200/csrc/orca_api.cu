@@ -174,6 +174,10 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   // obstacle tables staged in shared memory when they are small (<= 256 vertex slots = 16 KB)
   const int slots = s->per_env ? args.envs_per_block * s->vert_stride : s->vert_stride;
   args.world_slots = (slots > 0 && slots <= 256) ? slots : 0;
+  // worlds of more than 32 agents: candidates come from an in-block uniform grid (cell = neighborDist + 0.1 %)
+  args.tile_grid_inv_cell = 0.f;
+  if (N > 32 && s->p.neighbor_dist > 0.f && std::getenv("ORCA_B200_NO_TILE_GRID") == nullptr)
+    args.tile_grid_inv_cell = 1.0f / (s->p.neighbor_dist * 1.001f);
   const size_t smem = orca::step_smem_bytes(K, tpb, true, args.world_slots);
   auto kern = orca::step_small_kernel<K, KFULL, POLICY>;
   static bool attr_set = false;  // per instantiation

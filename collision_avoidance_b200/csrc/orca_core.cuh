@@ -514,6 +514,7 @@ struct NearestK {
       }
     }
   }
+  ORCA_HD void finish() {}
   // Candidates arrive in arbitrary order (uniform-grid cells): order by (distance, rank) where
   // `precedes(a, b)` says whether entry a goes before entry b at equal distance (b may be -1 = empty
   // slot, which nothing precedes).  Gives the same list as ascending-id visiting.
@@ -535,6 +536,71 @@ struct NearestK {
         prev_d = old_d;
         prev_i = old_i;
       }
+    }
+  }
+};
+
+// ---- k-nearest list as 64-bit keys -------------------------------------------------------------------
+// Same list as NearestK, held as one integer key per slot: (distSq bits << 32) | (id + 1).
+// distSq >= +0, so its float bits order like the values and a single unsigned 64-bit compare IS
+// the (distance, id) order -- equal distances rank by id whatever order the candidates arrive
+// in (needed when they come cell by cell; for an ascending-id scan it equals RVO2's "first
+// visited wins").  Insertion is one pass of compare-exchange: every slot keeps min(slot, carry)
+// and hands max(slot, carry) on, the largest key falls off the end -- 6 instructions per slot
+// with the tie rule included, against ~11 for the compare + rank-by-id + shift form.
+// Empty slot = (rangeSq bits << 32): a candidate at exactly rangeSq (id + 1 >= 1) is not below it,
+// which is RVO2's strict range test.  Slots >= k hold 0 and never accept anything.
+template <int K, bool KFULL>
+struct NearestKeys {
+  unsigned long long key[K];
+  int id[K];       // valid after finish() / set_sorted_ids()
+  float d[K];      // not maintained (distances are recomputed where they are reported)
+  int k;
+  float range_sq;
+  ORCA_HD void init(int k_, float range_sq_) {
+    k = k_;
+    range_sq = range_sq_;
+    const unsigned long long empty = (unsigned long long)(unsigned)float_to_bits(range_sq_) << 32;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      key[s] = (KFULL || s < k) ? empty : 0ull;
+      id[s] = -1;
+      d[s] = 0.f;
+    }
+  }
+  // acceptance threshold: the distance of the k-th slot (the largest key of the list)
+  ORCA_HD float thresh() const {
+    unsigned long long m = key[K - 1];
+    if (!KFULL) {
+#pragma unroll
+      for (int s = 0; s < K - 1; ++s) m = key[s] > m ? key[s] : m;
+    }
+    return bits_to_float((int)(unsigned)(m >> 32));
+  }
+  ORCA_HD void offer(float cand_d, int cand_id) {
+    unsigned long long x = ((unsigned long long)(unsigned)float_to_bits(cand_d) << 32) | (unsigned)(cand_id + 1);
+    if (KFULL && !(x < key[K - 1])) return;  // not among the k best (any more): nothing moves
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const unsigned long long cur = key[s];
+      const bool in_front = x < cur;
+      key[s] = in_front ? x : cur;
+      x = in_front ? cur : x;
+    }
+  }
+  template <class Before>
+  ORCA_HD void offer_ranked(float cand_d, int cand_id, const Before&) {
+    offer(cand_d, cand_id);
+  }
+  ORCA_HD void finish() {
+#pragma unroll
+    for (int s = 0; s < K; ++s) id[s] = (int)(unsigned)(key[s] & 0xffffffffull) - 1;
+  }
+  ORCA_HD void set_sorted_ids(const uint4 packed, int cnt) {
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const unsigned w = (s < 4) ? packed.x : (s < 8) ? packed.y : (s < 12) ? packed.z : packed.w;
+      id[s] = (s < cnt) ? (int)((w >> ((s & 3) * 8)) & 255u) : -1;
     }
   }
 };

@@ -87,6 +87,8 @@ struct GridSource {
   int env_n0;  // global id of the env's first agent
   int self;    // sorted slot of the agent itself
 
+  template <int K, bool KFULL>
+  using List = NearestK<K, KFULL>;
   struct Before {
     const int* orig;
     ORCA_HD bool operator()(int a, int b) const { return b >= 0 && ORCA_LDG(&orig[a]) < ORCA_LDG(&orig[b]); }

@@ -91,15 +91,38 @@ struct StepArgs {
   // the device address space (orca_step_host), written by the kernel itself over PCIe
   float2* pos_mirror;
   float2* vel_mirror;
+  // 1 / cell side of the in-block neighbor grid (tile kernel, worlds of more than 32 agents); 0: off
+  float tile_grid_inv_cell;
 };
 
 // Where an agent's neighbor candidates come from.  TileSource: the pre-step snapshot of the
 // agent's own env in shared memory, candidates = every other agent of the env in id order.
+//
+// For worlds of more than 32 agents the block first bins its envs' agents into a small uniform
+// grid in shared memory (kTileGrid x kTileGrid cells of side neighborDist per env, anchored at
+// the env's bounding-box corner; see build_tile_grid): candidates = the agents of the 3 x 3 cells
+// around the agent -- about a fifth of a 256-agent dense crowd instead of all of it.  They no
+// longer arrive in id order, so equal distances are ranked by id explicitly (offer_ranked), which
+// gives the same list as the ascending-id scan.
+constexpr int kTileGrid = 8;                          // cells per side
+constexpr int kTileCells = kTileGrid * kTileGrid;     // 64
+constexpr int kTileStartStride = kTileCells + 2;      // cell_start row per env (u16), padded
+
 struct TileSource {
   const float2* env_pos;
   const float2* env_vel;
   int n;
   int self;
+  // in-block grid of this agent's env (nullptr: scan every agent of the env)
+  const unsigned short* cell_start = nullptr;  // [kTileCells + 1] exclusive prefix of the cell populations
+  const unsigned char* sorted = nullptr;       // [n] agent ids ordered by cell
+  int cx = 0, cy = 0;                          // the agent's own cell
+
+  struct LowerIdFirst {
+    ORCA_HD bool operator()(int a, int b) const { return b >= 0 && a < b; }
+  };
+  template <int K, bool KFULL>
+  using List = NearestKeys<K, KFULL>;
   // Worlds of at most 32 agents: rank every candidate by counting instead of inserting into a
   // sorted list.  rank(j) = number of candidates that go in front of j in (distSq, id) order;
   // the accepted neighbors are the in-range candidates of rank < k, already in RVO2's order
@@ -151,6 +174,7 @@ struct TileSource {
         const float2 q = env_pos[j];
         nk.offer(abs_sq(sub(p, q)), j);
       }
+      nk.finish();
       return;
     }
     CandidateBuffer buf;
@@ -158,6 +182,36 @@ struct TileSource {
     buf.stride = scratch.stride;
     buf.cap = scratch_slots;
     buf.cnt = 0;
+    if (cell_start != nullptr) {
+      LowerIdFirst before;
+      auto insert_ranked = [&nk, &before](float d, int id) { nk.offer_ranked(d, id, before); };
+      const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < kTileGrid ? cx + 1 : kTileGrid - 1;
+      // three rows of cells; the cells (x0..x1, row) have consecutive keys, i.e. they are one
+      // contiguous run of `sorted`.  Lanes walk their own runs but vote together every iteration.
+      // The agent's own row goes first: the nearest candidates tighten the threshold early.
+      for (int r = 0; r < 3; ++r) {
+        const int yy = cy + (r == 0 ? 0 : (r == 1 ? -1 : 1));
+        int q = 0, last = 0;
+        if (yy >= 0 && yy < kTileGrid) {
+          q = cell_start[yy * kTileGrid + x0];
+          last = cell_start[yy * kTileGrid + x1 + 1];
+        }
+        while (ORCA_ANY(mask, q < last)) {
+          if (q < last) {
+            const int j = sorted[q];
+            if (j != self) {
+              const float d = abs_sq(sub(p, env_pos[j]));
+              if (d <= nk.thresh()) buf.push(d, j);
+            }
+            ++q;
+          }
+          buf.drain_if_full(mask, insert_ranked);
+        }
+      }
+      buf.drain(mask, insert_ranked);
+      nk.finish();
+      return;
+    }
     auto insert = [&nk](float d, int id) { nk.offer(d, id); };
     for (int j = 0; j < n; ++j) {  // n is uniform over the warp's envs
       if (j != self) {
@@ -168,6 +222,7 @@ struct TileSource {
       buf.drain_if_full(mask, insert);
     }
     buf.drain(mask, insert);
+    nk.finish();
   }
   ORCA_HD float2 pos(int q) const { return env_pos[q]; }
   ORCA_HD float2 vel(int q) const { return env_vel[q]; }
@@ -297,7 +352,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
   int ocnt = 0;
   if (W.n_nodes > 0) obstacle_neighbors(W, p, a.obst_range_sq, od, oid, &ocnt, &overflow);
 
-  NearestK<K, KFULL> nk;
+  typename Src::template List<K, KFULL> nk;
   nk.init(a.k, a.nd_sq);
   src.gather(nk, p, L, K + ORCA_MAX_OBST_LINES, warp_mask);
 
@@ -464,8 +519,12 @@ inline size_t step_smem_bytes(int K, int tpb, bool tile, int world_slots = 0) {
 #endif
 template <int K>
 __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* s_meta, float2* s_nv,
-                                          unsigned short* s_queue, int* s_warp_cnt, const bool need, const AgentCarry& c, const float vmax) {
+                                          unsigned short* s_queue, int* s_warp_cnt, const bool need, const AgentCarry& c, const float vmax,
+                                          const bool area_was_borrowed = false) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  // the queue area doubled as the in-block neighbor grid during the front half: nobody may
+  // overwrite it while another warp still searches its neighbors
+  if (area_was_borrowed) __syncthreads();
 #if !ORCA_BLOCK_LP3
   {  // in-place variant (kept for A/B measurements): every thread solves its own agent
     Lines L;
@@ -551,6 +610,70 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
   __syncthreads();
 }
 
+// order-preserving float -> int mapping for the bounding-box atomicMin
+__device__ __forceinline__ int tile_float_to_ordered(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float tile_ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// Bins the agents of the block's envs into per-env kTileGrid x kTileGrid grids (counting sort in
+// shared memory) and points `src` at the tables of the thread's env.  `area` is the LP3 queue
+// area, free during the front half of the step: per env 64 counters + 2 bounding-box words +
+// 66 cell starts (u16), then one id byte per thread; 13 bytes per thread at most, the area has 14.
+// Cell side = neighborDist (+0.1 %), origin = the env's bounding-box corner; coordinates beyond
+// the last cell are clamped into it (a superset of the 3 x 3 neighborhood, never a subset).
+// The order of ids inside a cell depends on the order of the atomics; the neighbor list does not
+// (equal distances are ranked by id).  Called by every thread of the block.
+__device__ __forceinline__ void build_tile_grid(const StepArgs& a, void* area, const bool valid, const int le, const int la,
+                                                const float2 p, TileSource& src) {
+  const int tid = threadIdx.x, tpb = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = tpb >> 5;
+  const int envs = a.envs_per_block;
+  int* cnt = reinterpret_cast<int*>(area);
+  int* bbox = cnt + envs * kTileCells;
+  unsigned short* start = reinterpret_cast<unsigned short*>(bbox + envs * 2);
+  unsigned char* sorted = reinterpret_cast<unsigned char*>(start + envs * kTileStartStride);
+  for (int i = tid; i < envs * kTileCells; i += tpb) cnt[i] = 0;
+  if (tid < envs * 2) bbox[tid] = 0x7fffffff;
+  __syncthreads();
+  if (valid) {
+    atomicMin(&bbox[2 * le], tile_float_to_ordered(p.x));
+    atomicMin(&bbox[2 * le + 1], tile_float_to_ordered(p.y));
+  }
+  __syncthreads();
+  int ck = 0, slot = 0, cx = 0, cy = 0;
+  if (valid) {
+    const float ox = tile_ordered_to_float(bbox[2 * le]), oy = tile_ordered_to_float(bbox[2 * le + 1]);
+    cx = (int)floorf((p.x - ox) * a.tile_grid_inv_cell);
+    cy = (int)floorf((p.y - oy) * a.tile_grid_inv_cell);
+    cx = cx < 0 ? 0 : (cx >= kTileGrid ? kTileGrid - 1 : cx);
+    cy = cy < 0 ? 0 : (cy >= kTileGrid ? kTileGrid - 1 : cy);
+    ck = cy * kTileGrid + cx;
+    slot = atomicAdd(&cnt[le * kTileCells + ck], 1);
+  }
+  __syncthreads();
+  for (int e = warp; e < envs; e += nwarps) {  // exclusive scan of the 64 cell populations, 2 per lane
+    const int c0 = cnt[e * kTileCells + 2 * lane], c1 = cnt[e * kTileCells + 2 * lane + 1];
+    int incl = c0 + c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += up;
+    }
+    const int excl = incl - (c0 + c1);
+    start[e * kTileStartStride + 2 * lane] = (unsigned short)excl;
+    start[e * kTileStartStride + 2 * lane + 1] = (unsigned short)(excl + c0);
+    if (lane == 31) start[e * kTileStartStride + kTileCells] = (unsigned short)incl;
+  }
+  __syncthreads();
+  if (valid) sorted[le * a.N + start[le * kTileStartStride + ck] + slot] = (unsigned char)la;
+  __syncthreads();
+  src.cell_start = start + le * kTileStartStride;
+  src.sorted = sorted + le * a.N;
+  src.cx = cx;
+  src.cy = cy;
+}
+
 template <int K, bool KFULL, int POLICY>
 __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) step_small_kernel(const StepArgs a) {
   extern __shared__ float4 smem4[];
@@ -611,6 +734,9 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   __syncthreads();
   const unsigned warp_mask = __ballot_sync(0xffffffffu, valid);  // lanes that run the step
   bool alive = valid;
+  TileSource src;
+  const bool tile_grid = a.tile_grid_inv_cell > 0.f;  // uniform over the grid
+  if (tile_grid) build_tile_grid(a, s_nv, valid, le, la, c.p, src);
   if (valid) {
     ObstacleWorld W = global_world(a, env);
     if (slots > 0) {
@@ -623,7 +749,6 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
     Lines L;
     L.base = s_lines + tid;
     L.stride = tpb;
-    TileSource src;
     src.env_pos = s_pos + le * N;
     src.env_vel = s_vel + le * N;
     src.n = N;
@@ -631,7 +756,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
     alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, W, L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
-  block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);
+  block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax, tile_grid);
   if (!alive) return;
   c.nv = s_nv[tid];
   agent_back<POLICY>(a, env, la, g, estep, c);

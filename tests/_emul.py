@@ -33,7 +33,7 @@ class StepArgs(ctypes.Structure):
         ("stats", c_p),
         ("vert_pd", c_p), ("vert_link", c_p), ("bsp", c_p), ("bsp_seg", c_p), ("env_nodes", c_p),
         ("shared_nodes", c_i), ("vert_stride", c_i), ("world_slots", c_i), ("world_verts", c_i), ("neighbors_only", c_i), ("grid_path", c_i),
-        ("pos_mirror", c_p), ("vel_mirror", c_p),
+        ("pos_mirror", c_p), ("vel_mirror", c_p), ("tile_grid_inv_cell", c_f),
     ]
 
 
@@ -102,13 +102,18 @@ class World:
 def emul_step(params, pos, vel, *, policy=0, pref=None, goal=None, goal2=None, world=None, action_theta=None,
               rl_scale=0.3, done_x=2.0, alan_w=None, alan_actions=None, alan_uniform=None, alan_window=121,
               alan_gamma=0.6, alan_temp=0.2, seed=0, done_mode=0, agent_done=None, arrival=None, env_step=None,
-              env_done_cnt=None, want_neighbors=False, neighbors_only=False, stats=None, grid=False):
+              env_done_cnt=None, want_neighbors=False, neighbors_only=False, stats=None, grid=False, tile_grid=None):
     """Run one fused step on host arrays, in place.  pos/vel: float32 [E, N, 2].
     Returns dict with optional outputs (reward, action, nbr_idx, nbr_cnt, ...)."""
     E, N = pos.shape[0], pos.shape[1]
     a = StepArgs()
     a.E, a.N, a.envs_per_block, a.k = E, N, 1, int(params["max_neighbors"])
     f32 = np.float32
+    # as launch_small_kp (csrc/orca_api.cu): worlds of more than 32 agents search an in-block grid
+    if tile_grid is None:
+        tile_grid = N > 32 and N <= 256 and not grid
+    nd = f32(params["neighbor_dist"])
+    a.tile_grid_inv_cell = f32(1.0) / (nd * f32(1.001)) if (tile_grid and nd > 0) else f32(0.0)
     dt = f32(params["time_step"])
     a.dt = dt
     a.inv_dt = f32(1.0) / dt

@@ -28,6 +28,28 @@ void run_k(const orca::StepArgs& a, int policy) {
       svel[(size_t)i] = a.vel[(size_t)e * N + i];
     }
     const int estep = a.env_step ? a.env_step[e] : 0;
+    // host twin of build_tile_grid (orca_step_small.cuh): same cells, ids inside a cell in
+    // DESCENDING id order here -- any order is legal, and this one differs from the id scan
+    std::vector<unsigned short> cell_start(orca::kTileCells + 1, 0);
+    std::vector<unsigned char> sorted((size_t)N);
+    std::vector<int> cell_of((size_t)N);
+    const bool tile_grid = a.tile_grid_inv_cell > 0.f;
+    if (tile_grid) {
+      float ox = INFINITY, oy = INFINITY;
+      for (int i = 0; i < N; ++i) { ox = std::fmin(ox, spos[(size_t)i].x); oy = std::fmin(oy, spos[(size_t)i].y); }
+      std::vector<int> cnt(orca::kTileCells, 0);
+      for (int i = 0; i < N; ++i) {
+        int cx = (int)floorf((spos[(size_t)i].x - ox) * a.tile_grid_inv_cell);
+        int cy = (int)floorf((spos[(size_t)i].y - oy) * a.tile_grid_inv_cell);
+        cx = cx < 0 ? 0 : (cx >= orca::kTileGrid ? orca::kTileGrid - 1 : cx);
+        cy = cy < 0 ? 0 : (cy >= orca::kTileGrid ? orca::kTileGrid - 1 : cy);
+        cell_of[(size_t)i] = cy * orca::kTileGrid + cx;
+        cnt[cell_of[(size_t)i]]++;
+      }
+      for (int c = 0; c < orca::kTileCells; ++c) cell_start[c + 1] = (unsigned short)(cell_start[c] + cnt[c]);
+      std::vector<int> fill(orca::kTileCells, 0);
+      for (int i = N - 1; i >= 0; --i) sorted[cell_start[cell_of[(size_t)i]] + fill[cell_of[(size_t)i]]++] = (unsigned char)i;
+    }
     for (int i = 0; i < N; ++i) {
       orca::Lines L;
       L.base = lines.data();
@@ -38,6 +60,12 @@ void run_k(const orca::StepArgs& a, int policy) {
       src.env_vel = svel.data();
       src.n = N;
       src.self = i;
+      if (tile_grid) {
+        src.cell_start = cell_start.data();
+        src.sorted = sorted.data();
+        src.cx = cell_of[(size_t)i] % orca::kTileGrid;
+        src.cy = cell_of[(size_t)i] / orca::kTileGrid;
+      }
       switch (policy) {
         case 0: orca::agent_step_body<K, KFULL, 0>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, src, L, 0xffffffffu); break;
         case 1: orca::agent_step_body<K, KFULL, 1>(a, e, i, g, spos[(size_t)i], svel[(size_t)i], estep, src, L, 0xffffffffu); break;

@@ -188,3 +188,26 @@ def test_host_entry_point_pipelined_chunks_equal_single_launch(monkeypatch, chun
     a.env_step(policy=_lib.POLICY_GOAL, goal=goal)
     b.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
     assert np.array_equal(a.pos.cpu().numpy(), pos_h.numpy().reshape(E, N, 2))
+
+
+@pytest.mark.parametrize("E,N,blocks", [(9, 33, 0), (11, 48, 0), (3, 200, 0), (4, 256, 4), (5, 100, 4)])
+def test_in_block_grid_equals_id_scan_on_gpu(monkeypatch, E, N, blocks):
+    """Tile kernel, worlds of more than 32 agents: candidates from the in-block uniform grid
+    (default) vs the plain scan over every agent of the env (ORCA_B200_NO_TILE_GRID) -- same bits
+    after a long run, several envs per block included."""
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    scn = scenarios.crowd(E, N, seed=7 * N + E, blocks=blocks)
+    goal = torch.from_numpy(scn.goal).cuda()
+    a = _mk(scn)
+    monkeypatch.setenv("ORCA_B200_NO_TILE_GRID", "1")
+    b = _mk(scn)
+    for t in range(150):
+        monkeypatch.delenv("ORCA_B200_NO_TILE_GRID", raising=False)
+        a.env_step(policy=_lib.POLICY_GOAL, goal=goal, want_neighbors=(t % 50 == 0))
+        monkeypatch.setenv("ORCA_B200_NO_TILE_GRID", "1")
+        b.env_step(policy=_lib.POLICY_GOAL, goal=goal, want_neighbors=(t % 50 == 0))
+        if t % 50 == 0:
+            assert torch.equal(a.nbr_idx, b.nbr_idx) and torch.equal(a.nbr_cnt, b.nbr_cnt)
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.vel, b.vel)
+    assert a.read_stats() == b.read_stats()

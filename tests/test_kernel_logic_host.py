@@ -125,3 +125,36 @@ def test_equal_distances_keep_first_visited_order():
                     assert [x[0] for x in o] == list(out["nbr_idx"][e, i, :out["nbr_cnt"][e, i]])
             assert np.array_equal(ve, np.stack([s.velocities() for s in sims]))
         assert ties > 50
+
+
+def test_in_block_grid_gives_the_id_scan_lists():
+    """Worlds of more than 32 agents take their candidates from the in-block uniform grid
+    (TileSource with cell tables) in cell order; the neighbor lists -- order included, exact ties
+    included -- and the step results must be those of the plain ascending-id scan.  Covers a
+    symmetric ring (many bit-equal distances), a dense crowd, a world much wider than 8 cells
+    (border cells clamp) and k smaller than the in-range count."""
+    cases = []
+    ring = scenarios.circle(1, 48, seed=1, rotate=False)
+    cases.append((ring, 10))
+    cases.append((scenarios.crowd(1, 256, seed=2, blocks=4), 4))
+    wide = scenarios.crowd(1, 120, seed=3)
+    wide.pos = (wide.pos * 4.0).astype(np.float32)          # extent ~ 88 = 17 cells of 5: clamped border cells
+    wide.goal = (wide.goal * 4.0).astype(np.float32)
+    wide.obstacles = []
+    cases.append((wide, 6))
+    tight = scenarios.crowd(1, 64, seed=4)
+    tight.params = dict(tight.params, maxNeighbors=3, neighborDist=6.0)
+    cases.append((tight, 8))
+    for scn, steps in cases:
+        P = snake(scn.params)
+        W = _emul.World(scn.obstacles if not scn.per_env_obstacles else scn.obstacles[0])
+        pos_a, vel_a = scn.pos.copy(), scn.vel.copy()
+        for _ in range(steps):
+            pref = goal_pref(pos_a, scn.goal).astype(np.float32)
+            pos_b, vel_b = pos_a.copy(), vel_a.copy()
+            out_a = _emul.emul_step(P, pos_a, vel_a, policy=0, pref=pref, world=W, want_neighbors=True, tile_grid=True)
+            out_b = _emul.emul_step(P, pos_b, vel_b, policy=0, pref=pref, world=W, want_neighbors=True, tile_grid=False)
+            assert np.array_equal(out_a["nbr_cnt"], out_b["nbr_cnt"])
+            assert np.array_equal(out_a["nbr_idx"], out_b["nbr_idx"])
+            assert np.array_equal(out_a["nbr_dsq"], out_b["nbr_dsq"])
+            assert np.array_equal(pos_a, pos_b) and np.array_equal(vel_a, vel_b)

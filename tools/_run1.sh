@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_policy.py -m gpu -x -q 2>&1 | tail -5
-python tools/bench_policy.py
+ncu --set full --clock-control none --import-source on -k regex:step_small -s 120 -c 1 -f -o gpurun_out/prof_cfg4g python tools/bench_configs.py cfg4 > gpurun_out/ncu4.log 2>&1
+tail -n 1 gpurun_out/ncu4.log
