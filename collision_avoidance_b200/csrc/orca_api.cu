@@ -542,9 +542,10 @@ int orca_observe(OrcaSim* s, const float* pos_dev, const float* vel_dev, const f
     a.poly[i] = make_float2((float)((double)s->p.radius * std::cos(th)), (float)(-(double)s->p.radius * std::sin(th)));
   }
   const long long total = (long long)s->E * s->N * laser_num;
-  const int tpb = 256;
-  const long long blocks = (total + tpb - 1) / tpb;
-  orca::observe_kernel<<<(unsigned)blocks, tpb, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (total >= (1ll << 31)) return fail(ORCA_ERR_UNSUPPORTED, "orca_observe: E * N * laser_num must be below 2^31");
+  const int apb = orca::obs_agents_per_block(laser_num);  // whole agents per block: their rays share staged data
+  const long long blocks = ((long long)s->E * s->N + apb - 1) / apb;
+  orca::observe_kernel<<<(unsigned)blocks, orca::kObsThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, apb);
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;
   return ORCA_OK;

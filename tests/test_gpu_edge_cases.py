@@ -211,3 +211,35 @@ def test_in_block_grid_equals_id_scan_on_gpu(monkeypatch, E, N, blocks):
             assert torch.equal(a.nbr_idx, b.nbr_idx) and torch.equal(a.nbr_cnt, b.nbr_cnt)
     assert torch.equal(a.pos, b.pos) and torch.equal(a.vel, b.vel)
     assert a.read_stats() == b.read_stats()
+
+
+@pytest.mark.parametrize("R,C", [(16, 8), (12, 6), (5, 3), (32, 16), (1, 8), (9, 5)])
+def test_observation_kernel_equals_its_host_twin(R, C):
+    """observe_kernel (block-staged, queue of (ray, neighbor) pairs) against the serial host twin
+    of the same functions (tests/host_emul), for ray / polygon counts other than the default 16 / 8:
+    whole agents per block (21 for 12 rays, 32 for 5 ...), ragged last block, per-env obstacles,
+    k = 10 neighbor lists.  Same float32 operations in the same order -> identical bits."""
+    import torch
+    import _emul
+    from _common import snake
+    from collision_avoidance_b200 import _lib, scenarios
+    scn = scenarios.crowd(7, 23, seed=31 + R, blocks=4)
+    scn.params = dict(scn.params, neighborDist=3.0)
+    sim = _mk(scn)
+    goal = torch.from_numpy(scn.goal).cuda()
+    for _ in range(25):
+        sim.env_step(policy=_lib.POLICY_GOAL, goal=goal, want_neighbors=True)
+    obs = sim.observe(goal, laser_num=R, circle_approx_num=C).cpu().numpy()
+    pos, vel = sim.pos.cpu().numpy(), sim.vel.cpu().numpy()
+    P = snake(scn.params)
+    hits = 0
+    for e in range(scn.num_envs):
+        nbr = {"nbr_idx": np.ascontiguousarray(sim.nbr_idx[e:e + 1].cpu().numpy()),
+               "nbr_cnt": np.ascontiguousarray(sim.nbr_cnt[e:e + 1].cpu().numpy()),
+               "onbr_idx": np.ascontiguousarray(sim.obst_nbr_idx[e:e + 1].cpu().numpy()),
+               "onbr_cnt": np.ascontiguousarray(sim.obst_nbr_cnt[e:e + 1].cpu().numpy())}
+        ref = _emul.emul_observe(P, pos[e:e + 1].copy(), vel[e:e + 1].copy(), scn.goal[e:e + 1].copy(), nbr,
+                                 world=_emul.World(scn.obstacles[e]), laser_num=R, circle_approx_num=C)
+        assert np.array_equal(ref, obs[e:e + 1]), (e, float(np.abs(ref - obs[e:e + 1]).max()))
+        hits += int((np.abs(ref).reshape(-1, 4)[:, :2].sum(-1) > 0).sum())
+    assert hits > 0 or R == 1

@@ -158,3 +158,47 @@ def test_in_block_grid_gives_the_id_scan_lists():
             assert np.array_equal(out_a["nbr_idx"], out_b["nbr_idx"])
             assert np.array_equal(out_a["nbr_dsq"], out_b["nbr_dsq"])
             assert np.array_equal(pos_a, pos_b) and np.array_equal(vel_a, vel_b)
+
+
+def test_observation_logic_matches_shell_oracle():
+    """Host twin of observe_kernel (cull -> pair tests -> winner, csrc/orca_obs.cuh) against the
+    float64 shell (collision_avoidence_env.py:231-350 + utils.py) on the default gym world:
+    same hit / miss pattern up to grazing rays, hit points and velocities within 2e-4."""
+    from collision_avoidance_b200 import scenarios as S
+    from oracle.shell_oracle import EnvShellOracle
+    E, N, steps = 2, 10, 120
+    scn = S.default_env(E, N, seed=21)
+    P = snake(scn.params)
+    W = _emul.World(scn.obstacles)
+    shells = [EnvShellOracle(scn, e) for e in range(E)]
+    for e, sh in enumerate(shells):
+        sh.reset(scn.pos[e])
+    rng = np.random.default_rng(9)
+    worst = 0.0
+    flips = rays = hits = 0
+    for t in range(steps):
+        pre = np.stack([s.sim.positions() for s in shells]).astype(np.float32)
+        theta = rng.uniform(-0.6, 0.6, (E, N)).astype(np.float32)
+        outs = [sh.step(theta[e]) for e, sh in enumerate(shells)]
+        post_p = np.stack([s.sim.positions() for s in shells]).astype(np.float32)
+        post_v = np.stack([s.sim.velocities() for s in shells]).astype(np.float32)
+        goal = np.array([s.targets for s in shells], np.float32)
+        o_obs = np.array([o[0] for o in outs]).reshape(E, N, 16, 4)
+        for e in range(E):
+            # neighbor lists of the step (pre-update positions), state after the step (SURVEY Q3)
+            pp, vv = pre[e:e + 1].copy(), post_v[e:e + 1].copy()
+            nbr = _emul.emul_step(P, pp, vv, policy=0, pref=np.zeros((1, N, 2), np.float32), world=W,
+                                  want_neighbors=True, neighbors_only=True)
+            g_obs = _emul.emul_observe(P, post_p[e:e + 1].copy(), post_v[e:e + 1].copy(), goal[e:e + 1].copy(), nbr,
+                                       world=W).reshape(N, 16, 4)
+            hit_g = np.abs(g_obs[..., :2]).sum(-1) > 0
+            hit_o = np.abs(o_obs[e][..., :2]).sum(-1) > 0
+            agree = hit_g == hit_o
+            flips += int((~agree).sum())
+            rays += agree.size
+            hits += int(hit_o.sum())
+            if agree.any():
+                worst = max(worst, float(np.abs(g_obs - o_obs[e])[agree].max()))
+    assert hits > 0.1 * rays          # the scans are not trivially empty
+    assert worst <= 2e-4
+    assert flips <= 0.002 * rays
