@@ -33,7 +33,7 @@ MAX_ACTIONS = 16
 EXPORTED_SYMBOLS = (
     "orca_abi_version", "orca_last_error", "orca_create", "orca_destroy", "orca_get_params",
     "orca_set_obstacles", "orca_obstacle_vertex_count", "orca_get_obstacle_vertices",
-    "orca_step", "orca_env_step", "orca_env_step_many", "orca_neighbors", "orca_observe", "orca_step_host", "orca_policy_mlp", "orca_launch_count",
+    "orca_step", "orca_env_step", "orca_env_step_many", "orca_neighbors", "orca_observe", "orca_step_host", "orca_policy_mlp", "orca_policy_mlp_fp32", "orca_launch_count",
 )
 
 
@@ -135,6 +135,7 @@ def load() -> ctypes.CDLL:
     L.orca_observe.argtypes = [hp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, i, i, _vp, _vp]
     L.orca_step_host.argtypes = [hp, _vp, _vp, _vp, i, i, i]
     L.orca_policy_mlp.argtypes = [hp, _vp, ctypes.c_int64, ctypes.POINTER(OrcaMlpWeights), _vp, _vp]
+    L.orca_policy_mlp_fp32.argtypes = [hp, _vp, ctypes.c_int64, ctypes.POINTER(OrcaMlpWeights), _vp, _vp]
     L.orca_launch_count.argtypes = [hp]
     L.orca_launch_count.restype = ctypes.c_int64
     for name in EXPORTED_SYMBOLS:

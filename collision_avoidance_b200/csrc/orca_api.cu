@@ -22,6 +22,7 @@
 #include "orca_grid.cuh"
 #include "orca_obs.cuh"
 #include "orca_policy.cuh"
+#include "orca_policy_tc.cuh"
 #include "orca_step_small.cuh"
 
 namespace {
@@ -768,7 +769,11 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
   return rc;
 }
 
-int orca_policy_mlp(OrcaSim* s, const float* obs_dev, int64_t rows, const OrcaMlpWeights* w, float* out_dev, void* stream) {
+}  // extern "C"
+
+namespace {
+int policy_mlp_common(OrcaSim* s, const float* obs_dev, int64_t rows, const OrcaMlpWeights* w, float* out_dev, void* stream,
+                      bool tensor_cores) {
   if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
   if (w == nullptr || obs_dev == nullptr || out_dev == nullptr) return fail(ORCA_ERR_INVALID, "orca_policy_mlp: null pointer argument");
   if (w->struct_size != sizeof(OrcaMlpWeights)) return fail(ORCA_ERR_INVALID, "OrcaMlpWeights.struct_size mismatch");
@@ -800,15 +805,33 @@ int orca_policy_mlp(OrcaSim* s, const float* obs_dev, int64_t rows, const OrcaMl
   static int sm_count = 0;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(orca::policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::mlp_smem_bytes()));
+    CUDA_TRY(cudaFuncSetAttribute(orca::policy_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::mlp_tc_smem_bytes()));
     CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, s->device));
     attr_set = true;
   }
-  const long long tiles = (rows + orca::kMlpTile - 1) / orca::kMlpTile;
-  const int blocks = (int)std::min<long long>(tiles, 2ll * sm_count);  // persistent: 2 resident blocks per SM
-  orca::policy_mlp_kernel<<<blocks, orca::kMlpThreads, orca::mlp_smem_bytes(), static_cast<cudaStream_t>(stream)>>>(a);
+  if (tensor_cores) {
+    const long long tiles = (rows + orca::kTcTile - 1) / orca::kTcTile;
+    // persistent: one CTA per SM (195 KB of shared memory), two tile pipelines per CTA
+    const int blocks = (int)std::min<long long>((tiles + orca::kTcGroups - 1) / orca::kTcGroups, sm_count);
+    orca::policy_mlp_tc_kernel<<<blocks, orca::kTcThreads, orca::mlp_tc_smem_bytes(), static_cast<cudaStream_t>(stream)>>>(a);
+  } else {
+    const long long tiles = (rows + orca::kMlpTile - 1) / orca::kMlpTile;
+    const int blocks = (int)std::min<long long>(tiles, 2ll * sm_count);  // persistent: 2 resident blocks per SM
+    orca::policy_mlp_kernel<<<blocks, orca::kMlpThreads, orca::mlp_smem_bytes(), static_cast<cudaStream_t>(stream)>>>(a);
+  }
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;
   return ORCA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int orca_policy_mlp(OrcaSim* s, const float* obs_dev, int64_t rows, const OrcaMlpWeights* w, float* out_dev, void* stream) {
+  return policy_mlp_common(s, obs_dev, rows, w, out_dev, stream, true);
+}
+int orca_policy_mlp_fp32(OrcaSim* s, const float* obs_dev, int64_t rows, const OrcaMlpWeights* w, float* out_dev, void* stream) {
+  return policy_mlp_common(s, obs_dev, rows, w, out_dev, stream, false);
 }
 
 int64_t orca_launch_count(const OrcaSim* s) { return s ? s->launches : 0; }

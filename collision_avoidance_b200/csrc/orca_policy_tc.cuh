@@ -1,0 +1,344 @@
+// orca_policy_tc.cuh -- the shared policy network (orca_policy.cuh) on the 5th-generation tensor
+// cores: tcgen05.mma with TMEM accumulators, hand-written for sm_100a.
+//
+// This is the one dense contraction next to the ORCA path: for every agent
+//     h1 = relu(obs . W1 + b1) ; h2 = relu(h1 . W2 + b2) ; out = h2 . W3 + b3        (64-64-64-out)
+// i.e. two [rows x 64] x [64 x 64] GEMMs whose A operand is produced on chip.  On the FP32 pipes
+// (policy_mlp_kernel) it is FMA-bound at ~0.41 ms per million rows; here the products run as
+// tcgen05.mma kind::tf32 and the kernel is bound by reading the observations once.
+//
+// Accuracy: a single TF32 product drops 13 mantissa bits of each operand (~1e-3 relative), too
+// coarse for a parity target of 1e-4 on O(1) outputs.  Every product is therefore split
+//     a = a_hi + a_lo,  w = w_hi + w_lo      (x_hi = x with the low 13 mantissa bits cleared)
+//     a . w  ~=  a_hi . w_hi + a_hi . w_lo + a_lo . w_hi                 ("3xTF32")
+// accumulated in FP32 in TMEM: error ~2^-21 relative per product, the same order as FP32 itself.
+// Tensor-core time triples and still hides behind the HBM read.
+//
+// One CTA = two independent groups of 128 threads; a group = 128 agents (one TMEM lane each),
+// persistent over row tiles.  The groups share the weight tiles and nothing else (own A tiles, own
+// accumulator columns, own mbarrier, named barriers): while one waits for its MMAs the other runs
+// its epilogue, so the four schedulers of the SM always have a warp with work.  Per group:
+//   - weights (B operands): split once per CTA into K-major SWIZZLE_NONE core-matrix layout in
+//     shared memory, 4 x 16 KB;
+//   - the A operand lives in TENSOR MEMORY (tcgen05.mma with A from TMEM): row r of the tile is
+//     TMEM lane r, which is exactly what thread r owns -- it splits its own observation row
+//     (prefetched into registers during the previous tile's MMAs) and writes a_hi / a_lo with
+//     tcgen05.st, no shared-memory staging, no proxy fence.  With N = 64 an MMA that fetches A from
+//     shared memory is bound by that fetch (4 KB of A + 2 KB of B per 128x64x8 MMA, measured 53 ns
+//     each); from TMEM only the 2 KB of B cross the shared-memory port;
+//   - one thread issues 8 k-steps x 3 tcgen05.mma (M = 128, N = 64, K = 8) and commits to an
+//     mbarrier; every thread then pulls ITS row of the accumulator with tcgen05.ld, adds the bias,
+//     applies ReLU, splits again and stores the row back as the A operand of the second GEMM; the
+//     64 -> out head is a handful of FMAs on the registers that tcgen05.ld delivered.
+// Tensor memory per group: a_hi 64 + a_lo 64 + accumulator 64 columns; shared memory ~67 KB.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "orca_policy.cuh"
+
+namespace orca {
+
+constexpr int kTcTile = 128;     // rows per CTA tile = MMA M = TMEM lanes
+constexpr int kTcGroups = 2;     // independent 128-thread pipelines per CTA
+constexpr int kTcThreads = 128 * kTcGroups;
+constexpr int kTcN = 64;         // MMA N = hidden width
+constexpr int kTcK = 64;         // reduction length of both GEMMs
+constexpr int kTcAccCols = 3 * kTcN;         // per group: a_hi | a_lo | accumulator, 64 columns each
+constexpr int kTcTmemCols = 512;             // power of two >= kTcGroups * kTcAccCols
+
+// byte sizes / strides of the K-major SWIZZLE_NONE operand tiles: a core matrix is 8 rows x 16 B
+// (4 tf32), stored as 128 contiguous bytes; core matrices of consecutive 8-row groups follow each
+// other (SBO = 128 B), the next 16-byte chunk along K starts after all row groups (LBO).
+constexpr uint32_t kTcSbo = 128;
+constexpr uint32_t kTcLboB = (kTcN / 8) * 128;     // 1024
+constexpr uint32_t kTcBytesB = kTcN * kTcK * 4;     // 16 KB
+
+inline size_t mlp_tc_smem_bytes() {
+  return 4 * (size_t)kTcBytesB + sizeof(float) * (kMlpHidden * kMlpMaxOut + 2 * kMlpHidden + kMlpMaxOut) +
+         64 /* mbarrier + tmem base */ + 1024 /* alignment slack */;
+}
+
+#if defined(__CUDACC__)
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor (SM100 UMMA, version 1), SWIZZLE_NONE, K-major
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address, bits [0, 14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;    // leading-dimension byte offset, bits [16, 30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;    // stride-dimension byte offset, bits [32, 46)
+  d |= (uint64_t)1 << 46;                               // descriptor version 1 (Blackwell)
+  return d;                                             // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 64, dense, no negate
+__device__ __forceinline__ uint32_t make_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// A operand from tensor memory (lane = row, column = k), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t zero = 0u;  // disable-output-lane mask: none
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(zero)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;\n" ::"r"(group + 1) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// this thread's row (64 floats in v) -> its TMEM lane of the a_hi (columns [0, 64)) and a_lo
+// (columns [64, 128)) operands of the group
+__device__ __forceinline__ void store_row_split(uint32_t lane_base, const float* v) {
+#pragma unroll
+  for (int q = 0; q < kTcK / 16; ++q) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      hi[i] = tf32_hi(v[16 * q + i]);
+      lo[i] = v[16 * q + i] - hi[i];
+    }
+    tmem_st16(lane_base + (uint32_t)(16 * q), hi);
+    tmem_st16(lane_base + (uint32_t)(kTcN + 16 * q), lo);
+  }
+  tmem_st_wait();
+}
+
+// D[tmem] = A . B over K = 64 with the 3xTF32 split: 8 k-steps x 3 MMAs (issued by ONE thread).
+// tmem_group: first column of the group (a_hi | a_lo | D), lane 0.
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_group, uint32_t b_hi, uint32_t b_lo, uint32_t idesc) {
+  const uint32_t d = tmem_group + 2u * (uint32_t)kTcN;
+#pragma unroll
+  for (int ks = 0; ks < kTcK / 8; ++ks) {  // one MMA consumes K = 8 tf32: 8 TMEM columns of A, two 16-byte chunks of B
+    const uint32_t ah = tmem_group + (uint32_t)(8 * ks), al = ah + (uint32_t)kTcN;
+    const uint64_t dbh = make_desc(b_hi + (uint32_t)ks * 2u * kTcLboB, kTcLboB, kTcSbo);
+    const uint64_t dbl = make_desc(b_lo + (uint32_t)ks * 2u * kTcLboB, kTcLboB, kTcSbo);
+    mma_tf32_ts(d, al, dbh, idesc, ks > 0 ? 1u : 0u);  // small terms first
+    mma_tf32_ts(d, ah, dbl, idesc, 1u);
+    mma_tf32_ts(d, ah, dbh, idesc, 1u);
+  }
+}
+
+}  // namespace tc
+
+__global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpArgs a) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int group = tid >> 7, gtid = tid & 127;  // pipeline of this thread, row of the tile / TMEM lane
+  uint8_t* w1_hi = base;
+  uint8_t* w1_lo = w1_hi + kTcBytesB;
+  uint8_t* w2_hi = w1_lo + kTcBytesB;
+  uint8_t* w2_lo = w2_hi + kTcBytesB;
+  float* w3 = reinterpret_cast<float*>(w2_lo + kTcBytesB);  // [64][n_out]
+  float* b1 = w3 + kMlpHidden * kMlpMaxOut;
+  float* b2 = b1 + kMlpHidden;
+  float* b3 = b2 + kMlpHidden;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b3 + kMlpMaxOut);  // one per group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTcGroups);
+  uint64_t* bar = bars + group;
+
+  // ---- one-time setup: weights (split, K-major core-matrix layout), barrier, TMEM ----
+  for (int i = tid; i < kTcK * kTcN; i += kTcThreads) {
+    const int k = i >> 6, n = i & 63;  // global [k][n] (n contiguous): coalesced reads
+    const uint32_t off = (uint32_t)(k >> 2) * kTcLboB + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 3) * 4u;
+    const float x1 = __ldg(a.w1 + i), x2 = __ldg(a.w2 + i);
+    const float h1 = tc::tf32_hi(x1), h2 = tc::tf32_hi(x2);
+    *reinterpret_cast<float*>(w1_hi + off) = h1;
+    *reinterpret_cast<float*>(w1_lo + off) = x1 - h1;
+    *reinterpret_cast<float*>(w2_hi + off) = h2;
+    *reinterpret_cast<float*>(w2_lo + off) = x2 - h2;
+  }
+  for (int i = tid; i < kMlpHidden * a.n_out; i += kTcThreads) w3[i] = __ldg(a.w3 + i);
+  if (tid < kMlpHidden) {
+    b1[tid] = __ldg(a.b1 + tid);
+    b2[tid] = __ldg(a.b2 + tid);
+  }
+  if (tid < a.n_out) b3[tid] = __ldg(a.b3 + tid);
+  if (tid == 0) {
+    for (int gq = 0; gq < kTcGroups; ++gq) tc::mbar_init(tc::smem_u32(bars + gq), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {  // one warp allocates the accumulator columns and passes the permit on
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc::smem_u32(tmem_slot)), "n"(kTcTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc::fence_async_smem();  // the weight tiles were written through the generic proxy, the MMA reads them through the async proxy
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_alloc = *tmem_slot;
+  const uint32_t tmem_base = tmem_alloc + (uint32_t)(group * kTcAccCols);  // this group's accumulator columns
+  const uint32_t idesc = tc::make_idesc();
+  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
+  const uint32_t s_w1_hi = tc::smem_u32(w1_hi), s_w1_lo = tc::smem_u32(w1_lo);
+  const uint32_t s_w2_hi = tc::smem_u32(w2_hi), s_w2_lo = tc::smem_u32(w2_lo);
+  const uint32_t s_bar = tc::smem_u32(bar);
+  uint32_t parity = 0;
+
+  const long long tiles = (a.rows + kTcTile - 1) / kTcTile;
+  float v[kTcK];  // this thread's row: observation, then h1, then h2
+
+  const long long first_tile = (long long)blockIdx.x * kTcGroups + group, tile_step = (long long)gridDim.x * kTcGroups;
+  // prefetch the first tile's row
+  {
+    const long long row = first_tile * kTcTile + gtid;
+#pragma unroll
+    for (int c = 0; c < kTcK / 4; ++c) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (first_tile < tiles && row < a.rows) x = __ldg(reinterpret_cast<const float4*>(a.obs + row * kMlpIn) + c);
+      v[4 * c + 0] = x.x;
+      v[4 * c + 1] = x.y;
+      v[4 * c + 2] = x.z;
+      v[4 * c + 3] = x.w;
+    }
+  }
+
+  for (long long tile = first_tile; tile < tiles; tile += tile_step) {
+    const long long row = tile * kTcTile + gtid;
+
+    // ---- GEMM 1: obs . W1 ----
+    tc::store_row_split(lane_base, v);
+    tc::fence_before_sync();
+    tc::group_sync(group);
+    if (gtid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm(tmem_base, s_w1_hi, s_w1_lo, idesc);
+      tc::mma_commit(s_bar);
+    }
+    // while the tensor core works: fetch the next tile's row of observations
+    float nxt[kTcK];
+    {
+      const long long nrow = (tile + tile_step) * kTcTile + gtid;
+      const bool have = (tile + tile_step) < tiles && nrow < a.rows;
+#pragma unroll
+      for (int c = 0; c < kTcK / 4; ++c) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+#if !defined(ORCA_TC_DEV_NO_LOAD)  // dev A/B: no observation traffic
+        if (have) x = __ldg(reinterpret_cast<const float4*>(a.obs + nrow * kMlpIn) + c);
+#endif
+        nxt[4 * c + 0] = x.x;
+        nxt[4 * c + 1] = x.y;
+        nxt[4 * c + 2] = x.z;
+        nxt[4 * c + 3] = x.w;
+      }
+    }
+    tc::mbar_wait(s_bar, parity);
+    parity ^= 1u;
+    tc::fence_after_sync();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tc::tmem_ld16(lane_base + (uint32_t)(2 * kTcN + 16 * q), v + 16 * q);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int n = 0; n < kTcN; ++n) v[n] = fmaxf(v[n] + b1[n], 0.f);
+
+    // ---- GEMM 2: h1 . W2 (the A columns are free: GEMM 1 has completed) ----
+    tc::store_row_split(lane_base, v);
+    tc::fence_before_sync();
+    tc::group_sync(group);
+    if (gtid == 0) {
+      tc::fence_after_sync();
+      tc::issue_gemm(tmem_base, s_w2_hi, s_w2_lo, idesc);
+      tc::mma_commit(s_bar);
+    }
+    tc::mbar_wait(s_bar, parity);
+    parity ^= 1u;
+    tc::fence_after_sync();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tc::tmem_ld16(lane_base + (uint32_t)(2 * kTcN + 16 * q), v + 16 * q);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int n = 0; n < kTcN; ++n) v[n] = fmaxf(v[n] + b2[n], 0.f);
+
+    // ---- head: 64 -> n_out on the registers ----
+    if (row < a.rows) {
+      for (int o = 0; o < a.n_out; ++o) {
+        float acc = b3[o];
+#pragma unroll
+        for (int n = 0; n < kTcN; ++n) acc = fmaf(v[n], w3[n * a.n_out + o], acc);
+        a.out[row * a.n_out + o] = acc;
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < kTcK; ++n) v[n] = nxt[n];
+  }
+
+  // ---- teardown ----
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_alloc), "n"(kTcTmemCols) : "memory");
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace orca

@@ -36,9 +36,12 @@ class SharedMLPPolicy:
     log-std.  Weight matrices are stored [in][out] like ``slim.fully_connected``.
     """
 
-    def __init__(self, sim, num_outputs: int = 2, seed: int = 0):
+    def __init__(self, sim, num_outputs: int = 2, seed: int = 0, impl: str = "tcgen05"):
         if not 1 <= num_outputs <= 8:
             raise NotImplementedError("num_outputs must be in [1, 8]")
+        if impl not in ("tcgen05", "fp32"):
+            raise ValueError("impl must be 'tcgen05' (tensor cores, 3xTF32) or 'fp32' (FP32 pipes)")
+        self.impl = impl
         self._sim = sim
         self._L = _lib.load()
         self.device = sim.device
@@ -86,8 +89,8 @@ class SharedMLPPolicy:
                                 self.w1.data_ptr(), self.b1.data_ptr(), self.w2.data_ptr(), self.b2.data_ptr(),
                                 self.w3.data_ptr(), self.b3.data_ptr())
         stream = torch.cuda.current_stream(obs.device).cuda_stream
-        _lib.check(self._L.orca_policy_mlp(self._sim._h, obs.data_ptr(), rows, ctypes.byref(w), out.data_ptr(),
-                                           ctypes.c_void_p(stream)))
+        fn = self._L.orca_policy_mlp if self.impl == "tcgen05" else self._L.orca_policy_mlp_fp32
+        _lib.check(fn(self._sim._h, obs.data_ptr(), rows, ctypes.byref(w), out.data_ptr(), ctypes.c_void_p(stream)))
         return out
 
     __call__ = forward

@@ -206,9 +206,15 @@ typedef struct OrcaMlpWeights {
 /* Forward pass of that network for `rows` observation rows ([rows][64], e.g. the buffer
  * orca_observe wrote for E*N agents): out_dev[rows][out_dim].  Replaces the per-env TensorFlow
  * evaluation inside RLlib's rollout workers (run_rllib.py:35-52,96-112) so that
- * observe -> policy -> orca_env_step stays on the device.  Asynchronous on `stream`. */
+ * observe -> policy -> orca_env_step stays on the device.  Asynchronous on `stream`.
+ *   orca_policy_mlp       tcgen05 tensor cores, TF32 products split 3x (hi.hi + hi.lo + lo.hi),
+ *                         FP32 accumulation in TMEM: FP32-level accuracy, bound by reading obs once;
+ *   orca_policy_mlp_fp32  the same network on the FP32 pipes (fused multiply-adds), kept as the
+ *                         reference point for the tensor-core kernel. */
 int orca_policy_mlp(OrcaSim* sim, const float* obs_dev, int64_t rows, const OrcaMlpWeights* weights, float* out_dev,
                     void* stream);
+int orca_policy_mlp_fp32(OrcaSim* sim, const float* obs_dev, int64_t rows, const OrcaMlpWeights* weights, float* out_dev,
+                         void* stream);
 
 /* Host-buffer variant of orca_step (the e2e path: what a PyRVOSimulator-style caller
  * pays): takes pref / goal (and, if `upload_state`, pos/vel) from host buffers, steps `steps`
