@@ -18,3 +18,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 330 --csv --l
 ncu --set full --clock-control none --import-source on -k regex:step_small -s 120 -c 2 -f -o gpurun_out/prof_${TAG}_step \
   python bench.py --steps 150 --warmup 20 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
 tail -2 gpurun_out/ncu2.log
+python tools/bench_policy.py > gpurun_out/policy_${TAG}.jsonl 2> gpurun_out/policy_err.log; cat gpurun_out/policy_${TAG}.jsonl
+ncu --set full --clock-control none --import-source on -k regex:policy_mlp_tc -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_policy_tc \
+  python tools/bench_policy.py > gpurun_out/ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:observe -s 100 -c 1 -f -o gpurun_out/prof_${TAG}_obs \
+  python tools/bench_configs.py env > gpurun_out/ncu4.log 2>&1
+python tools/obs_time.py 2>/dev/null | tail -1

@@ -53,4 +53,46 @@ json.dump({"step_small_kernel_dram_bytes_per_launch": sum(tr) / len(tr),
            "algorithmic_bytes_per_launch": 41 * 65536 * 16}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 with open(os.path.join(P, f"{tag}_step_small_by_function.txt"), "w") as f:
     subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep, KERNEL], stdout=f)
+# other kernels of the round: raw metrics + per-function breakdown + tensor-core SASS evidence
+EXTRA = {"policy_tc": ("_ZN4orca20policy_mlp_tc_kernelENS_7MlpArgsE", "policy_mlp_tc_kernel"),
+         "obs": ("_ZN4orca14observe_kernelENS_7ObsArgsEi", "observe_kernel")}
+for short, (mangled, nice) in EXTRA.items():
+    rep2 = os.path.join(G, f"prof_{tag}_{short}.ncu-rep")
+    if not os.path.exists(rep2):
+        continue
+    raw2 = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows2 = list(csv.reader(raw2.splitlines()))
+    h2, u2 = rows2[0], rows2[1]
+    with open(os.path.join(P, f"{tag}_{short}_ncu_raw.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + [f"launch{i}" for i in range(len(rows2) - 2)])
+        for k in KEYS + ["sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+                         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]:
+            if k in h2:
+                i = h2.index(k)
+                w.writerow([k, u2[i]] + [r[i] for r in rows2[2:]])
+    with open(os.path.join(P, f"{tag}_{short}_by_function.txt"), "w") as f:
+        subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep2, mangled], stdout=f)
+if os.path.exists(os.path.join(G, f"policy_{tag}.jsonl")):
+    shutil.copy(os.path.join(G, f"policy_{tag}.jsonl"), os.path.join(P, f"{tag}_policy_kernels.jsonl"))
+if os.path.exists(os.path.join(G, f"bench_{tag}_n2.json")):
+    shutil.copy(os.path.join(G, f"bench_{tag}_n2.json"), os.path.join(P, f"{tag}_bench_n2.json"))
+# SASS mnemonics of the tensor-core kernel (tcgen05.mma / tcgen05.ld / tcgen05.st / commit / alloc)
+lib = os.path.join(ROOT, "collision_avoidance_b200", "liborca_b200.so")
+sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+on, counts = False, {}
+for ln in sass.splitlines():
+    if "Function :" in ln:
+        on = "policy_mlp_tc" in ln
+    elif on:
+        for m in ("UTCMMA", "UTCBAR", "LDTM", "STTM", "UTCATOMSWS", "SYNCS", "UTCHMMA", "UTCQMMA"):
+            if m in ln:
+                op = [t for t in ln.split() if t.startswith(m)]
+                if op:
+                    counts[op[0].rstrip(";")] = counts.get(op[0].rstrip(";"), 0) + 1
+with open(os.path.join(P, f"{tag}_policy_tc_sass_mnemonics.txt"), "w") as f:
+    f.write("cuobjdump -sass liborca_b200.so, function policy_mlp_tc_kernel: tensor-core / tensor-memory instructions\n")
+    for k in sorted(counts):
+        f.write(f"{counts[k]:4d}  {k}\n")
 print(open(os.path.join(P, "traffic.json")).read())
