@@ -1,2 +1,2 @@
-timeout 300 python -m pytest tests/test_gpu_policy.py -m gpu -x -q 2>&1 | tail -3
-timeout 120 python tools/bench_policy.py
+python tools/bench_configs.py cfg2 cfg4 2>&1 | cut -c1-110
+for f in _alt/liblp3_*.so; do echo $f; ORCA_B200_LIB=$PWD/$f python tools/bench_configs.py cfg2 cfg4 2>&1 | cut -c1-110; done
