@@ -1,2 +1,2 @@
-python tools/bench_configs.py cfg2 cfg4 2>&1 | cut -c1-110
-for f in _alt/liblp3_*.so; do echo $f; ORCA_B200_LIB=$PWD/$f python tools/bench_configs.py cfg2 cfg4 2>&1 | cut -c1-110; done
+ncu --set full --clock-control none --import-source on -k regex:step_small -s 120 -c 1 -f -o gpurun_out/prof_cfg2p python bench.py --steps 150 --warmup 20 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
+tail -n 1 gpurun_out/ncu2.log
