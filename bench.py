@@ -58,6 +58,23 @@ def _traffic():
     return None
 
 
+def _issue_profile():
+    """What actually bounds the step kernel (same ncu capture): issue-slot use, warp-instructions
+    per launch and live lanes per instruction.  Reported next to the HBM roofline, which this
+    kernel cannot approach."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    if "step_small_kernel_issue_active_pct" not in t:
+        return None
+    return {"issue_slots_busy_frac": t["step_small_kernel_issue_active_pct"] / 100.0,
+            "warp_instructions_per_launch": t["step_small_kernel_warp_instructions_per_launch"],
+            "active_lanes_per_instruction": t["step_small_kernel_active_lanes_per_instruction"],
+            "source": "profiles/r01_step_small_ncu_raw.csv (ncu --set full, bench step ~100)"}
+
+
 class ClockSampler:
     """Samples SM clocks + throttle reasons (NVML, every few ms) while the timed region runs."""
 
@@ -330,7 +347,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(), "peak_source": peak_src,
                          "bytes_per_agent_step": BYTES_PER_AGENT_STEP, "kernel": "step_small_kernel<10,GOAL>",
-                         "note": "kernel is FP32-issue bound, not HBM bound; see DESIGN.md Roofline"},
+                         "note": "kernel is instruction-issue / latency bound, not HBM bound; see DESIGN.md Roofline",
+                         "issue_profile": _issue_profile()},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_state,
                     "d2h_bytes_per_step": 2 * bytes_state, "steps": e2e_steps,
                     "api": "BatchedRVOSimulator.step_host -> orca_step_host (pinned host buffers; the library keeps the faster of its two routes: kernel reads/writes the mapped host buffers directly, or chunked upload | step | download over streams)"},

@@ -186,10 +186,11 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
     args.tile_grid_inv_cell = 1.0f / (s->p.neighbor_dist * 1.001f);
   const size_t smem = orca::step_smem_bytes(K, tpb, true, args.world_slots);
   auto kern = orca::step_small_kernel<K, KFULL, POLICY>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  // function attributes are per device: one flag per (instantiation, device)
+  static bool attr_set[orca::kMaxDevices] = {};
+  if (s->device >= orca::kMaxDevices || !attr_set[s->device]) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::step_smem_bytes(K, 256, true, 256)));
-    attr_set = true;
+    if (s->device < orca::kMaxDevices) attr_set[s->device] = true;
   }
   kern<<<blocks, tpb, smem, st>>>(args);
   CUDA_TRY(cudaGetLastError());
@@ -801,13 +802,13 @@ int policy_mlp_common(OrcaSim* s, const float* obs_dev, int64_t rows, const Orca
   a.b3 = w->b3_dev;
   a.n_out = w->out_dim;
   a.out = out_dev;
-  static bool attr_set = false;
-  static int sm_count = 0;
-  if (!attr_set) {
+  static bool attr_set[orca::kMaxDevices] = {};  // function attributes are per device
+  int sm_count = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, s->device));
+  if (s->device >= orca::kMaxDevices || !attr_set[s->device]) {
     CUDA_TRY(cudaFuncSetAttribute(orca::policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::mlp_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(orca::policy_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::mlp_tc_smem_bytes()));
-    CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, s->device));
-    attr_set = true;
+    if (s->device < orca::kMaxDevices) attr_set[s->device] = true;
   }
   if (tensor_cores) {
     const long long tiles = (rows + orca::kTcTile - 1) / orca::kTcTile;

@@ -454,10 +454,12 @@ int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* 
   const int stpb = 128;
   const size_t smem = step_smem_bytes(K, stpb, false);
   auto kern = step_grid_kernel<K, KFULL, POLICY>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};  // function attributes are per device
+  int dev = 0;
+  ORCA_GRID_TRY(cudaGetDevice(&dev));
+  if (dev >= kMaxDevices || !attr_set[dev]) {
     ORCA_GRID_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    if (dev < kMaxDevices) attr_set[dev] = true;
   }
   args.grid_path = 1;
   kern<<<(T + stpb - 1) / stpb, stpb, smem, st>>>(args, G.sorted_pos, G.sorted_vel, G.sorted_idx, G.cell_start, G.params);

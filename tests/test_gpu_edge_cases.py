@@ -243,3 +243,25 @@ def test_observation_kernel_equals_its_host_twin(R, C):
         assert np.array_equal(ref, obs[e:e + 1]), (e, float(np.abs(ref - obs[e:e + 1]).max()))
         hits += int((np.abs(ref).reshape(-1, 4)[:, :2].sum(-1) > 0).sum())
     assert hits > 0 or R == 1
+
+
+def test_handles_on_two_devices_in_one_process():
+    """Kernel attributes (dynamic shared memory opt-in) are per device: a second handle on another
+    GPU of the same process must launch just like the first.  Skipped on single-GPU boxes."""
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    from collision_avoidance_b200.sim import BatchedRVOSimulator
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    scn = scenarios.circle(40, 16, seed=5)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        sim = BatchedRVOSimulator(scn.num_envs, scn.agents_per_env, device=dev, **scn.params)
+        sim.set_obstacles(scn.obstacles)
+        sim.pos.copy_(torch.from_numpy(scn.pos))
+        sim.vel.copy_(torch.from_numpy(scn.vel))
+        goal = torch.from_numpy(scn.goal).to(dev)
+        for _ in range(30):
+            sim.env_step(policy=_lib.POLICY_GOAL, goal=goal)
+        outs.append(sim.pos.cpu())
+    assert torch.equal(outs[0], outs[1])

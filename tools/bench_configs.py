@@ -6,7 +6,8 @@
   cfg3  circle 32 agents x 32,768 envs (the per-GPU share of 262,144 over 8), ALAN, 8 actions
   cfg4  crowd 256 agents + 4 blocks x 2,048 envs (share of 16,384 over 8), ORCA policy
   cfg5  crowd 1,000,000 agents, one env, uniform grid
-  env   default gym world 10 agents x 100,000 envs, RL step + laser observation
+  env   default gym world 10 agents x 100,000 envs, RL step + laser observation; and the closed
+        loop observation -> policy network -> step
 Prints one JSON line per config: agent-steps/s, us/step, algorithmic-byte HBM fraction."""
 import json
 import os
@@ -84,6 +85,15 @@ def main():
         theta = (torch.rand(E, N, device="cuda", generator=torch.Generator("cuda").manual_seed(5)) - 0.5) * 0.6
         report("gym env 10 agents x100000 RL step + obs", E * N, timed(lambda: env.step(theta), steps, warmup), 45 + 256,
                env.sim.read_stats())
+        # the closed loop of the RL shell: observation -> shared policy network (tcgen05) -> fused step
+        from collision_avoidance_b200.policy import SharedMLPPolicy
+        pol = SharedMLPPolicy(env.sim, seed=1)
+        state = {"obs": env._get_obs()}
+
+        def loop_step():
+            state["obs"] = env.step(pol.act(state["obs"]))[0]
+        report("gym env 10 agents x100000 RL loop: obs + policy net + step", E * N, timed(loop_step, steps, warmup),
+               45 + 256 + 264, env.sim.read_stats())
 
 
 if __name__ == "__main__":

@@ -48,7 +48,17 @@ def nbytes(r, k):
 
 
 tr = [nbytes(r, "dram__bytes_read.sum") + nbytes(r, "dram__bytes_write.sum") for r in rows[2:]]
+def fnum(r, k):
+    return float(r[h.index(k)].replace(",", "")) if k in h else None
+
+
+issue = [fnum(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") for r in rows[2:]]
+winst = [fnum(r, "smsp__inst_executed.sum") for r in rows[2:]]
+lanes = [fnum(r, "smsp__thread_inst_executed_per_inst_executed.ratio") for r in rows[2:]]
 json.dump({"step_small_kernel_dram_bytes_per_launch": sum(tr) / len(tr),
+           "step_small_kernel_issue_active_pct": sum(issue) / len(issue),
+           "step_small_kernel_warp_instructions_per_launch": sum(winst) / len(winst),
+           "step_small_kernel_active_lanes_per_instruction": sum(lanes) / len(lanes),
            "source": f"profiles/{tag}_step_small_ncu_raw.csv (ncu --set full on bench.py, step ~100, {len(tr)} launches)",
            "algorithmic_bytes_per_launch": 41 * 65536 * 16}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 with open(os.path.join(P, f"{tag}_step_small_by_function.txt"), "w") as f:
