@@ -49,6 +49,9 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_RESULT_OUT = sys.stdout  # replaced in main() by a private duplicate of the real stdout
+
+
 def _traffic():
     """dram bytes per launch of the step kernel from the committed ncu --set full capture."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
@@ -228,7 +231,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -360,7 +363,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.steps, args.warmup)
             line["cpu_baseline_python_driver"] = cpu_python_driver_baseline()
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -374,6 +377,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries may write there too (NCCL prints its
+    # version banner to stdout when NCCL_DEBUG is set, as on the GPU boxes): keep a private handle on
+    # the real stdout for the line and point fd 1 at stderr for everything else.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
