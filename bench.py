@@ -319,7 +319,7 @@ def run_ours(args):
     # same episode phase as the kernel-timed region: W steps from the reset state, then K timed
     e2e_steps = max(3, args.steps)
     sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=max(1, args.warmup))
-    for _ in range(6):  # untimed: the library times both of its routes (direct / staged) on calls 2 and 4 and keeps the faster
+    for _ in range(8):  # untimed: the library times both of its routes (direct / staged) on its first six steady calls and keeps the faster
         sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
     barrier()
     t0 = time.perf_counter()

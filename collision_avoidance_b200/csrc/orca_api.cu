@@ -744,8 +744,8 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
   const bool may_direct = std::getenv("ORCA_B200_HOST_NO_MAPPED") == nullptr;
   // Which route is faster depends on the host (PCIe write efficiency of GPU stores vs copy-engine
   // bursts; measured 0.39 vs 0.45 ms on one box, 0.51 vs 0.45 ms on another).  Both give the same
-  // bits, so steady-state calls (same buffers, one step, no state upload) time each route twice
-  // and keep the faster one.
+  // bits, so steady-state calls (same buffers, one step, no state upload) time each route three
+  // times and keep the faster one.
   const bool steady = may_direct && upload_state == 0 && steps == 1 && std::getenv("ORCA_B200_HOST_NO_AUTOTUNE") == nullptr;
   if (!steady) return step_host_route(s, pos_host, vel_host, pref_or_goal_host, policy, upload_state, steps, may_direct);
   HostGraphKey key{pos_host, vel_host, pref_or_goal_host, policy, 0, 1, 0};
@@ -754,18 +754,26 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
     s->tune_calls = 0;
     s->tune_ms[0] = s->tune_ms[1] = 0.0;
   }
+  // calls 0-2: direct, calls 3-5: staged; the first call of each route warms it up (graph capture,
+  // first touch), the faster of the other two is the route's time
+  constexpr int kTunePerRoute = 3;
   bool direct;
-  if (s->tune_calls < 4) {
-    direct = s->tune_calls < 2;  // calls 0, 1: direct; calls 2, 3: staged; the second of each pair is timed
+  if (s->tune_calls < 2 * kTunePerRoute) {
+    direct = s->tune_calls < kTunePerRoute;
   } else {
     direct = s->tune_ms[0] <= s->tune_ms[1];
   }
   const auto t0 = std::chrono::steady_clock::now();
   const int rc = step_host_route(s, pos_host, vel_host, pref_or_goal_host, policy, upload_state, steps, direct);
-  if (s->tune_calls < 4) {
+  if (s->tune_calls < 2 * kTunePerRoute) {
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (s->tune_calls & 1) s->tune_ms[s->tune_calls >> 1] = ms;
+    const int route = s->tune_calls / kTunePerRoute, nth = s->tune_calls % kTunePerRoute;
+    if (nth == 1) s->tune_ms[route] = ms;
+    if (nth == 2) s->tune_ms[route] = std::min(s->tune_ms[route], ms);
     s->tune_calls += 1;
+    if (s->tune_calls == 2 * kTunePerRoute && std::getenv("ORCA_B200_HOST_TRACE") != nullptr)
+      std::fprintf(stderr, "orca_step_host: direct %.3f ms, staged %.3f ms -> %s\n", s->tune_ms[0], s->tune_ms[1],
+                   s->tune_ms[0] <= s->tune_ms[1] ? "direct" : "staged");
   }
   return rc;
 }
