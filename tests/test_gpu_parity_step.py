@@ -246,3 +246,51 @@ def test_exact_ties_keep_first_visited_order_on_gpu():
                     assert [x[0] for x in o] == list(idx[e, i, :cnt[e, i]]), (N, k, e, i)
             assert np.array_equal(gpu.vel.cpu().numpy(), np.stack([s.velocities() for s in sims]))
         assert ties > 50
+
+
+@pytest.mark.parametrize("name,small_envs,copies,agents,steps", [("cfg2", 64, 1024, 16, 60), ("cfg4", 16, 128, 256, 25)])
+def test_full_size_batches_are_env_independent(name, small_envs, copies, agents, steps):
+    """BASELINE configs[1] (65,536 envs x 16 agents) and the per-GPU share of configs[3] (2,048 envs
+    x 256 agents with per-env obstacle blocks) at FULL size, through a size-independent property:
+    envs never interact, so a batch made of `copies` copies of a few distinct envs must give every
+    copy the bits of the small batch -- which the cases above pin to the oracle step by step --
+    wherever the copy sits in the batch (block boundaries, last block, 32-bit offsets)."""
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    from collision_avoidance_b200.sim import BatchedRVOSimulator
+    if name == "cfg2":
+        scn = scenarios.circle(small_envs, agents, seed=21)
+    else:
+        scn = scenarios.crowd(small_envs, agents, seed=22, blocks=4)
+    small = _gpu_sim(scn)
+    E = small_envs * copies
+    big = BatchedRVOSimulator(E, agents, device="cuda:0", **scn.params)
+    if scn.per_env_obstacles:
+        big.set_obstacles(list(scn.obstacles) * copies, per_env=True)
+    else:
+        big.set_obstacles(scn.obstacles, per_env=False)
+    big.pos.copy_(torch.from_numpy(np.tile(scn.pos, (copies, 1, 1))))
+    big.vel.copy_(torch.from_numpy(np.tile(scn.vel, (copies, 1, 1))))
+    g_s = torch.from_numpy(scn.goal).cuda()
+    g_b = torch.from_numpy(np.tile(scn.goal, (copies, 1, 1))).cuda()
+    # one step from the shared initial state against the oracle (1e-4, north star) ...
+    sims = oracle_sims(scn)
+    pref = goal_pref(scn.pos, scn.goal).astype(np.float32)
+    for e, s in enumerate(sims):
+        s.set_pref_velocities(pref[e])
+        s.doStep()
+    small.env_step(policy=_lib.POLICY_GOAL, goal=g_s)
+    big.env_step(policy=_lib.POLICY_GOAL, goal=g_b)
+    ov = np.stack([s.velocities() for s in sims])
+    assert np.abs(small.vel.cpu().numpy() - ov).max() <= TOL
+    # ... then a closed-loop run: every copy keeps the bits of the small batch
+    for _ in range(steps):
+        small.env_step(policy=_lib.POLICY_GOAL, goal=g_s)
+        big.env_step(policy=_lib.POLICY_GOAL, goal=g_b)
+    sp, sv = small.pos.cpu().numpy(), small.vel.cpu().numpy()
+    bp = big.pos.cpu().numpy().reshape(copies, small_envs, agents, 2)
+    bv = big.vel.cpu().numpy().reshape(copies, small_envs, agents, 2)
+    assert np.array_equal(bp, np.broadcast_to(sp, bp.shape))
+    assert np.array_equal(bv, np.broadcast_to(sv, bv.shape))
+    st_s, st_b = small.read_stats(), big.read_stats()
+    assert st_b["collisions"] == copies * st_s["collisions"] and st_b["lp3_calls"] == copies * st_s["lp3_calls"]
