@@ -248,6 +248,10 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: run on (and pin host buffers from) the cores next to that GPU
+    from collision_avoidance_b200.dist import bind_to_gpu_numa
+    # (only with several ranks: at N=1 the CPU baseline below wants every host core)
+    cores = bind_to_gpu_numa(local_rank) if world > 1 and not os.environ.get("BENCH_NO_AFFINITY") else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -357,6 +361,8 @@ def run_ours(args):
                     "api": "BatchedRVOSimulator.step_host -> orca_step_host (pinned host buffers; the library keeps the faster of its two routes: kernel reads/writes the mapped host buffers directly, or chunked upload | step | download over streams)"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
+            "host_affinity": {"rank0_cores": len(cores) if cores else None,
+                              "note": "each rank runs on the cores NVML lists next to its GPU" if cores else "not bound"},
             "wall_s_timed_region": wall,
             "episode_stats": stats_d,
         }

@@ -17,6 +17,39 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[list]:
+    """Pin this process to the CPU cores next to GPU ``device_index`` (NVML's cpu affinity of the
+    device = the cores of its NUMA node / PCIe root).  One process drives one GPU; host buffers it
+    pins afterwards are first-touched on that node, so the per-step host<->device traffic of
+    ``orca_step_host`` does not cross the socket interconnect when several ranks run at once.
+    Returns the cores bound to, or None when NVML or the affinity call is unavailable (no-op)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device_index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if device_index < len(ids) and ids[device_index].isdigit():
+                    idx = int(ids[device_index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cores = [w * 64 + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1]
+        finally:
+            pynvml.nvmlShutdown()
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(c for c in cores if c in allowed)
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 def shard_range(num_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous env range [start, start + count) owned by ``rank``; sizes differ by at most 1."""
     if not 0 <= rank < world_size:

@@ -89,3 +89,15 @@ def test_stats_all_reduce_world_size_2_gloo():
 def test_all_reduce_is_noop_without_process_group():
     x = torch.arange(5, dtype=torch.float64)
     assert torch.equal(cdist.all_reduce_stats(x.clone()), x)
+
+
+def test_numa_binding_is_a_noop_without_a_gpu():
+    """bind_to_gpu_numa never raises: without NVML / a GPU it reports None and leaves the affinity alone."""
+    import os
+    from collision_avoidance_b200.dist import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    cores = bind_to_gpu_numa(0)
+    assert cores is None or set(cores) <= before
+    if cores is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
