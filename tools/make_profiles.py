@@ -23,6 +23,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "launch__waves_per_multiprocessor", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.avg"]
+KEYS += [f"smsp__average_warps_issue_stalled_{r}_per_issue_active.ratio" for r in
+         ("barrier", "wait", "no_instruction", "branch_resolving", "long_scoreboard", "short_scoreboard",
+          "math_pipe_throttle", "not_selected")]
 
 shutil.copy(os.path.join(G, f"launches_{tag}.csv"), os.path.join(P, f"{tag}_launches.csv"))
 shutil.copy(os.path.join(G, f"bench_{tag}.json"), os.path.join(P, f"{tag}_bench_n1.json"))
@@ -63,6 +66,13 @@ json.dump({"step_small_kernel_dram_bytes_per_launch": sum(tr) / len(tr),
            "algorithmic_bytes_per_launch": 41 * 65536 * 16}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 with open(os.path.join(P, f"{tag}_step_small_by_function.txt"), "w") as f:
     subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep, KERNEL], stdout=f)
+with open(os.path.join(P, f"{tag}_step_small_by_callpath.txt"), "w") as f:  # same, keyed by inline call path
+    subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ncu_phases.py"), rep, KERNEL, "3"], stdout=f)
+for n in (2, 4, 8):
+    for arm, suffix in (("", ""), ("_ref", "_reference_arm")):
+        src = os.path.join(G, f"bench_{tag}_n{n}{arm}.json")
+        if os.path.exists(src):
+            shutil.copy(src, os.path.join(P, f"{tag}_bench_n{n}{suffix}.json"))
 # other kernels of the round: raw metrics + per-function breakdown + tensor-core SASS evidence
 EXTRA = {"policy_tc": ("_ZN4orca20policy_mlp_tc_kernelENS_7MlpArgsE", "policy_mlp_tc_kernel"),
          "obs": ("_ZN4orca14observe_kernelENS_7ObsArgsEi", "observe_kernel")}
@@ -86,8 +96,6 @@ for short, (mangled, nice) in EXTRA.items():
         subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep2, mangled], stdout=f)
 if os.path.exists(os.path.join(G, f"policy_{tag}.jsonl")):
     shutil.copy(os.path.join(G, f"policy_{tag}.jsonl"), os.path.join(P, f"{tag}_policy_kernels.jsonl"))
-if os.path.exists(os.path.join(G, f"bench_{tag}_n2.json")):
-    shutil.copy(os.path.join(G, f"bench_{tag}_n2.json"), os.path.join(P, f"{tag}_bench_n2.json"))
 # SASS mnemonics of the tensor-core kernel (tcgen05.mma / tcgen05.ld / tcgen05.st / commit / alloc)
 lib = os.path.join(ROOT, "collision_avoidance_b200", "liborca_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
