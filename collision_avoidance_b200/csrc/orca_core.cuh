@@ -463,9 +463,12 @@ struct NearestK {
   int id[K];
   int k;           // runtime maxNeighbors (<= K)
   float range_sq;  // neighborDist^2
+  uint4 packed;    // the sorted ids as bytes, when a caller handed the list over ready-made
+  int packed_cnt;  // number of ids in `packed`; -1: the list lives in id[] only
   ORCA_HD void init(int k_, float range_sq_) {
     k = k_;
     range_sq = range_sq_;
+    packed_cnt = -1;
 #pragma unroll
     for (int s = 0; s < K; ++s) {
       d[s] = (KFULL || s < k) ? range_sq : -1.0f;
@@ -474,10 +477,12 @@ struct NearestK {
   }
   // The list handed over ready-made by a caller that ranked its candidates itself: the id of slot
   // s in byte s of `packed` (16 bytes), slots 0..cnt-1 valid.  Distances are not kept.
-  ORCA_HD void set_sorted_ids(const uint4 packed, int cnt) {
+  ORCA_HD void set_sorted_ids(const uint4 packed_, int cnt) {
+    packed = packed_;
+    packed_cnt = cnt;
 #pragma unroll
     for (int s = 0; s < K; ++s) {
-      const unsigned w = (s < 4) ? packed.x : (s < 8) ? packed.y : (s < 12) ? packed.z : packed.w;
+      const unsigned w = (s < 4) ? packed_.x : (s < 8) ? packed_.y : (s < 12) ? packed_.z : packed_.w;
       id[s] = (s < cnt) ? (int)((w >> ((s & 3) * 8)) & 255u) : -1;
       d[s] = 0.f;
     }
@@ -557,9 +562,12 @@ struct NearestKeys {
   float d[K];      // not maintained (distances are recomputed where they are reported)
   int k;
   float range_sq;
+  uint4 packed;    // see NearestK
+  int packed_cnt;
   ORCA_HD void init(int k_, float range_sq_) {
     k = k_;
     range_sq = range_sq_;
+    packed_cnt = -1;
     const unsigned long long empty = (unsigned long long)(unsigned)float_to_bits(range_sq_) << 32;
 #pragma unroll
     for (int s = 0; s < K; ++s) {
@@ -596,10 +604,30 @@ struct NearestKeys {
 #pragma unroll
     for (int s = 0; s < K; ++s) id[s] = (int)(unsigned)(key[s] & 0xffffffffull) - 1;
   }
-  ORCA_HD void set_sorted_ids(const uint4 packed, int cnt) {
+  // ids below 256 (the tile kernel's in-env ids): also hand the list over as bytes, like
+  // set_sorted_ids does, so that its consumers can walk it with a rolled loop.  The valid entries
+  // are a prefix of the list (empty slots carry the largest key).
+  ORCA_HD void pack_ids() {
+    unsigned w[4] = {0u, 0u, 0u, 0u};
+    int cnt = 0;
 #pragma unroll
     for (int s = 0; s < K; ++s) {
-      const unsigned w = (s < 4) ? packed.x : (s < 8) ? packed.y : (s < 12) ? packed.z : packed.w;
+      const bool valid = id[s] >= 0;
+      w[s >> 2] |= valid ? ((unsigned)id[s] << ((s & 3) * 8)) : 0u;
+      cnt += valid ? 1 : 0;
+    }
+    packed.x = w[0];
+    packed.y = w[1];
+    packed.z = w[2];
+    packed.w = w[3];
+    packed_cnt = cnt;
+  }
+  ORCA_HD void set_sorted_ids(const uint4 packed_, int cnt) {
+    packed = packed_;
+    packed_cnt = cnt;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const unsigned w = (s < 4) ? packed_.x : (s < 8) ? packed_.y : (s < 12) ? packed_.z : packed_.w;
       id[s] = (s < cnt) ? (int)((w >> ((s & 3) * 8)) & 255u) : -1;
     }
   }

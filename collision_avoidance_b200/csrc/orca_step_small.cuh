@@ -212,6 +212,7 @@ struct TileSource {
       }
       buf.drain(mask, insert_ranked);
       nk.finish();
+      nk.pack_ids();
       return;
     }
     auto insert = [&nk](float d, int id) { nk.offer(d, id); };
@@ -225,6 +226,7 @@ struct TileSource {
     }
     buf.drain(mask, insert);
     nk.finish();
+    nk.pack_ids();
   }
   ORCA_HD float2 pos(int q) const { return env_pos[q]; }
   ORCA_HD float2 vel(int q) const { return env_vel[q]; }
@@ -384,15 +386,39 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
   unsigned collisions = 0;
   {
     const float cr = a.radius + a.radius;
-#pragma unroll
-    for (int s = 0; s < K; ++s) {
-      const int j = nk.id[s];
-      if (j >= 0) {
+#ifndef ORCA_UNROLLED_LINES  // A/B switch
+    if (nk.packed_cnt >= 0) {
+      // ranked selection (small worlds): the ids sit in `packed`, a byte each.  One ROLLED loop over
+      // them -- K unrolled copies of the half-plane construction are ~13 KB of straight-line code,
+      // a quarter of the hot instruction footprint of the kernel.
+      unsigned w0 = nk.packed.x, w1 = nk.packed.y, w2 = nk.packed.z, w3 = nk.packed.w;
+      const int cnt = nk.packed_cnt;
+#pragma unroll 1
+      for (int s = 0; s < cnt; ++s) {
+        const int j = (int)(w0 & 255u);
+        w0 = (w0 >> 8) | (w1 << 24);
+        w1 = (w1 >> 8) | (w2 << 24);
+        w2 = (w2 >> 8) | (w3 << 24);
+        w3 >>= 8;
         bool hit;
         const float4 ln = agent_line(p, v, src.pos(j), src.vel(j), cr, a.inv_th, a.inv_dt, &hit);
         L.base[n * L.stride] = ln;
         ++n;
         collisions += hit ? 1u : 0u;
+      }
+    } else
+#endif
+    {
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        const int j = nk.id[s];
+        if (j >= 0) {
+          bool hit;
+          const float4 ln = agent_line(p, v, src.pos(j), src.vel(j), cr, a.inv_th, a.inv_dt, &hit);
+          L.base[n * L.stride] = ln;
+          ++n;
+          collisions += hit ? 1u : 0u;
+        }
       }
     }
   }
