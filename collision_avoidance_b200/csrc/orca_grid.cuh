@@ -116,6 +116,7 @@ struct GridSource {
     const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < gp.W ? cx + 1 : gp.W - 1;
     // three rows of cells; the cells (x0..x1, row) are consecutive keys, i.e. one contiguous range
     // of the sorted arrays.  Lanes walk their own ranges but vote together on every iteration.
+#pragma unroll 1
     for (int dy = -1; dy <= 1; ++dy) {
       const int yy = cy + dy;
       int q = 0, last = 0;

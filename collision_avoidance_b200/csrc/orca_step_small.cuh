@@ -191,6 +191,7 @@ struct TileSource {
       // three rows of cells; the cells (x0..x1, row) have consecutive keys, i.e. they are one
       // contiguous run of `sorted`.  Lanes walk their own runs but vote together every iteration.
       // The agent's own row goes first: the nearest candidates tighten the threshold early.
+#pragma unroll 1
       for (int r = 0; r < 3; ++r) {
         const int yy = cy + (r == 0 ? 0 : (r == 1 ? -1 : 1));
         int q = 0, last = 0;
@@ -406,8 +407,24 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
         ++n;
         collisions += hit ? 1u : 0u;
       }
-    } else
-#endif
+    } else {
+      // ids that do not fit a byte (sorted slots of the uniform grid): the list goes through a small
+      // local-memory array so that the loop can still be rolled; its valid entries are a prefix
+      int ids[K];
+#pragma unroll
+      for (int s = 0; s < K; ++s) ids[s] = nk.id[s];
+#pragma unroll 1
+      for (int s = 0; s < K; ++s) {
+        const int j = ids[s];
+        if (j < 0) break;
+        bool hit;
+        const float4 ln = agent_line(p, v, src.pos(j), src.vel(j), cr, a.inv_th, a.inv_dt, &hit);
+        L.base[n * L.stride] = ln;
+        ++n;
+        collisions += hit ? 1u : 0u;
+      }
+    }
+#else
     {
 #pragma unroll
       for (int s = 0; s < K; ++s) {
@@ -421,6 +438,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
         }
       }
     }
+#endif
   }
   c.n = n;
   c.n_obst = n_obst;
