@@ -23,6 +23,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "launch__waves_per_multiprocessor", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.avg"]
+KEYS += ["sm__icc_request_hit_rate.pct", "sm__icc_requests.sum",
+         "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed"]  # instruction caches: SM, L1.5
 KEYS += [f"smsp__average_warps_issue_stalled_{r}_per_issue_active.ratio" for r in
          ("barrier", "wait", "no_instruction", "branch_resolving", "long_scoreboard", "short_scoreboard",
           "math_pipe_throttle", "not_selected")]
@@ -68,6 +70,8 @@ with open(os.path.join(P, f"{tag}_step_small_by_function.txt"), "w") as f:
     subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep, KERNEL], stdout=f)
 with open(os.path.join(P, f"{tag}_step_small_by_callpath.txt"), "w") as f:  # same, keyed by inline call path
     subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ncu_phases.py"), rep, KERNEL, "3"], stdout=f)
+with open(os.path.join(P, f"{tag}_step_small_hot_code.txt"), "w") as f:  # instruction-cache working set
+    subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ncu_hot_code.py"), rep, KERNEL, "2"], stdout=f)
 for n in (2, 4, 8):
     for arm, suffix in (("", ""), ("_ref", "_reference_arm")):
         src = os.path.join(G, f"bench_{tag}_n{n}{arm}.json")
