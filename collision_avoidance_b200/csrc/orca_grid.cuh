@@ -116,9 +116,12 @@ struct GridSource {
     const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < gp.W ? cx + 1 : gp.W - 1;
     // three rows of cells; the cells (x0..x1, row) are consecutive keys, i.e. one contiguous range
     // of the sorted arrays.  Lanes walk their own ranges but vote together on every iteration.
+    // The agent's own row goes first: the nearest candidates tighten the threshold early, so fewer of
+    // the later ones are parked and inserted (the list itself does not depend on the visiting order).
+    // (Own cell first, then the rest -- five runs instead of three -- measured slower: 601 vs 575 us.)
 #pragma unroll 1
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = cy + dy;
+    for (int r = 0; r < 3; ++r) {
+      const int yy = cy + (r == 0 ? 0 : (r == 1 ? -1 : 1));
       int q = 0, last = 0;
       if (yy >= 0 && yy < gp.H) {
         q = ORCA_LDG(&cell_start[base + yy * gp.W + x0]);
