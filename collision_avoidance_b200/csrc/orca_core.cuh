@@ -525,6 +525,15 @@ struct NearestK {
   // slot, which nothing precedes).  Gives the same list as ascending-id visiting.
   template <class Before>
   ORCA_HD void offer_ranked(float cand_d, int cand_id, const Before& precedes) {
+    // Bit-equal distances are rare: when no slot holds the candidate's distance the tie rule cannot
+    // fire and the plain insertion gives the same list without K conditional rank look-ups.
+    bool tie = false;
+#pragma unroll
+    for (int s = 0; s < K; ++s) tie = tie || (cand_d == d[s]);
+    if (!tie) {
+      offer(cand_d, cand_id);
+      return;
+    }
     if (cand_d <= thresh()) {
       bool prev_before = false;
       float prev_d = cand_d;
