@@ -127,14 +127,20 @@ struct GridSource {
         q = ORCA_LDG(&cell_start[base + yy * gp.W + x0]);
         last = ORCA_LDG(&cell_start[base + yy * gp.W + x1 + 1]);
       }
+      // the position of the NEXT candidate is fetched while the current one is tested and parked:
+      // the load (L1 / L2 latency) is the longest single wait of this loop
+      float2 nxt = v2(0.f, 0.f);
+      if (q < last) nxt = ORCA_LDG(&spos[q]);
       while (ORCA_ANY(mask, q < last)) {
         if (q < last) {
-          if (q != self) {
-            const float2 o = ORCA_LDG(&spos[q]);
-            const float d = abs_sq(sub(p, o));
-            if (d <= nk.thresh()) buf.push(d, q);
-          }
+          const float2 o = nxt;
+          const int cur = q;
           ++q;
+          if (q < last) nxt = ORCA_LDG(&spos[q]);
+          if (cur != self) {
+            const float d = abs_sq(sub(p, o));
+            if (d <= nk.thresh()) buf.push(d, cur);
+          }
         }
         buf.drain_if_full(mask, insert);
       }

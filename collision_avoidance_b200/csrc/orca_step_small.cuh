@@ -410,18 +410,33 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
     } else {
       // ids that do not fit a byte (sorted slots of the uniform grid): the list goes through a small
       // local-memory array so that the loop can still be rolled; its valid entries are a prefix
-      int ids[K];
+      int ids[K + 1];
 #pragma unroll
       for (int s = 0; s < K; ++s) ids[s] = nk.id[s];
+      ids[K] = -1;
+      // the state of the NEXT neighbor is fetched (global memory here) while the current line is built
+      int j = ids[0];
+      float2 pj = v2(0.f, 0.f), vj = v2(0.f, 0.f);
+      if (j >= 0) {
+        pj = src.pos(j);
+        vj = src.vel(j);
+      }
 #pragma unroll 1
-      for (int s = 0; s < K; ++s) {
-        const int j = ids[s];
-        if (j < 0) break;
+      for (int s = 1; j >= 0; ++s) {
+        const int jn = ids[s];
+        float2 pn = pj, vn = vj;
+        if (jn >= 0) {
+          pn = src.pos(jn);
+          vn = src.vel(jn);
+        }
         bool hit;
-        const float4 ln = agent_line(p, v, src.pos(j), src.vel(j), cr, a.inv_th, a.inv_dt, &hit);
+        const float4 ln = agent_line(p, v, pj, vj, cr, a.inv_th, a.inv_dt, &hit);
         L.base[n * L.stride] = ln;
         ++n;
         collisions += hit ? 1u : 0u;
+        j = jn;
+        pj = pn;
+        vj = vn;
       }
     }
 #else
