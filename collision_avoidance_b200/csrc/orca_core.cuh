@@ -683,9 +683,10 @@ struct CandidateBuffer {
     cnt = 0;
   }
   // drain when some lane of the warp is full; call once per candidate by every lane of `mask`
+  // `room` = pushes a lane may make before the next call (callers that test several candidates per vote)
   template <class Insert>
-  ORCA_HD void drain_if_full(unsigned mask, const Insert& insert) {
-    if (ORCA_ANY(mask, cnt >= cap)) drain(mask, insert);
+  ORCA_HD void drain_if_full(unsigned mask, const Insert& insert, int room = 1) {
+    if (ORCA_ANY(mask, cnt + room > cap)) drain(mask, insert);
   }
 };
 

@@ -131,18 +131,23 @@ struct GridSource {
       // the load (L1 / L2 latency) is the longest single wait of this loop
       float2 nxt = v2(0.f, 0.f);
       if (q < last) nxt = ORCA_LDG(&spos[q]);
+      // two candidates per pair of warp votes (loop condition, buffer check): the votes were a third
+      // of this loop's instructions
       while (ORCA_ANY(mask, q < last)) {
-        if (q < last) {
-          const float2 o = nxt;
-          const int cur = q;
-          ++q;
-          if (q < last) nxt = ORCA_LDG(&spos[q]);
-          if (cur != self) {
-            const float d = abs_sq(sub(p, o));
-            if (d <= nk.thresh()) buf.push(d, cur);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (q < last) {
+            const float2 o = nxt;
+            const int cur = q;
+            ++q;
+            if (q < last) nxt = ORCA_LDG(&spos[q]);
+            if (cur != self) {
+              const float d = abs_sq(sub(p, o));
+              if (d <= nk.thresh()) buf.push(d, cur);
+            }
           }
         }
-        buf.drain_if_full(mask, insert);
+        buf.drain_if_full(mask, insert, 2);
       }
     }
     buf.drain(mask, insert);
