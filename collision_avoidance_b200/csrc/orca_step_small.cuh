@@ -199,16 +199,19 @@ struct TileSource {
           q = cell_start[yy * kTileGrid + x0];
           last = cell_start[yy * kTileGrid + x1 + 1];
         }
-        while (ORCA_ANY(mask, q < last)) {
-          if (q < last) {
-            const int j = sorted[q];
-            if (j != self) {
-              const float d = abs_sq(sub(p, env_pos[j]));
-              if (d <= nk.thresh()) buf.push(d, j);
+        while (ORCA_ANY(mask, q < last)) {  // two candidates per pair of warp votes
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (q < last) {
+              const int j = sorted[q];
+              if (j != self) {
+                const float d = abs_sq(sub(p, env_pos[j]));
+                if (d <= nk.thresh()) buf.push(d, j);
+              }
+              ++q;
             }
-            ++q;
           }
-          buf.drain_if_full(mask, insert_ranked);
+          buf.drain_if_full(mask, insert_ranked, 2);
         }
       }
       buf.drain(mask, insert_ranked);
