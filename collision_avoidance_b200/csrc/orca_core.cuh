@@ -480,10 +480,13 @@ struct NearestK {
   ORCA_HD void set_sorted_ids(const uint4 packed_, int cnt) {
     packed = packed_;
     packed_cnt = cnt;
+  }
+  // id[] from the packed list (only the neighbor-list outputs read id[] on that path)
+  ORCA_HD void unpack_ids() {
 #pragma unroll
     for (int s = 0; s < K; ++s) {
-      const unsigned w = (s < 4) ? packed_.x : (s < 8) ? packed_.y : (s < 12) ? packed_.z : packed_.w;
-      id[s] = (s < cnt) ? (int)((w >> ((s & 3) * 8)) & 255u) : -1;
+      const unsigned w = (s < 4) ? packed.x : (s < 8) ? packed.y : (s < 12) ? packed.z : packed.w;
+      id[s] = (s < packed_cnt) ? (int)((w >> ((s & 3) * 8)) & 255u) : -1;
       d[s] = 0.f;
     }
   }
@@ -634,10 +637,13 @@ struct NearestKeys {
   ORCA_HD void set_sorted_ids(const uint4 packed_, int cnt) {
     packed = packed_;
     packed_cnt = cnt;
+  }
+  // id[] from the packed list (only the neighbor-list outputs read id[] on that path)
+  ORCA_HD void unpack_ids() {
 #pragma unroll
     for (int s = 0; s < K; ++s) {
-      const unsigned w = (s < 4) ? packed_.x : (s < 8) ? packed_.y : (s < 12) ? packed_.z : packed_.w;
-      id[s] = (s < cnt) ? (int)((w >> ((s & 3) * 8)) & 255u) : -1;
+      const unsigned w = (s < 4) ? packed.x : (s < 8) ? packed.y : (s < 12) ? packed.z : packed.w;
+      id[s] = (s < packed_cnt) ? (int)((w >> ((s & 3) * 8)) & 255u) : -1;
     }
   }
 };

@@ -365,6 +365,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
   src.gather(nk, p, L, K + ORCA_MAX_OBST_LINES, warp_mask);
 
   if (a.nbr_idx != nullptr) {
+    if (nk.packed_cnt >= 0) nk.unpack_ids();
     int cnt = 0;
 #pragma unroll
     for (int s = 0; s < K; ++s) {
@@ -444,6 +445,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
     }
 #else
     {
+      if (nk.packed_cnt >= 0) nk.unpack_ids();
 #pragma unroll
       for (int s = 0; s < K; ++s) {
         const int j = nk.id[s];
