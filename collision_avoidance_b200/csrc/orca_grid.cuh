@@ -335,10 +335,13 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float2* __restr
   sidx[j] = i;
 }
 
+#ifndef ORCA_GRID_TPB
+#define ORCA_GRID_TPB 64  // threads per block of the uniform-grid step kernel: 32 / 64 / 128 / 256 -> 466 / 469 / 483 / 506 us (cfg 5)
+#endif
 // G6: the fused step over the cell-sorted order.  Thread j handles the agent in sorted slot j, so a
 // warp's agents share cells (coherent candidate loops, cache-friendly reads).
 template <int K, bool KFULL, int POLICY>
-__global__ void __launch_bounds__(128, 6) step_grid_kernel(const StepArgs a, const float2* __restrict__ spos,
+__global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_kernel(const StepArgs a, const float2* __restrict__ spos,
                                                            const float2* __restrict__ svel, const int* __restrict__ sidx,
                                                            const int* __restrict__ cell_start,
                                                            const GridParams* __restrict__ gpp) {
@@ -466,7 +469,7 @@ int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* 
   StepArgs args = a;
   int* env_step = args.env_step;
   // the step kernel only READS the counters in this path (see grid_bump_env_step_kernel)
-  const int stpb = 128;
+  const int stpb = ORCA_GRID_TPB;
   const size_t smem = step_smem_bytes(K, stpb, false);
   auto kern = step_grid_kernel<K, KFULL, POLICY>;
   static bool attr_set[kMaxDevices] = {};  // function attributes are per device
