@@ -23,4 +23,6 @@ ncu --set full --clock-control none --import-source on -k regex:policy_mlp_tc -s
   python tools/bench_policy.py > gpurun_out/ncu3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:observe -s 100 -c 1 -f -o gpurun_out/prof_${TAG}_obs \
   python tools/bench_configs.py env > gpurun_out/ncu4.log 2>&1
+BC_STEPS=60 BC_WARMUP=20 ncu --set full --clock-control none --import-source on -k regex:step_grid -s 70 -c 1 -f -o gpurun_out/prof_${TAG}_grid \
+  python tools/bench_configs.py cfg5 > gpurun_out/ncu5.log 2>&1
 python tools/obs_time.py 2>/dev/null | tail -1

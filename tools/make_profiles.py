@@ -79,7 +79,9 @@ for n in (2, 4, 8):
             shutil.copy(src, os.path.join(P, f"{tag}_bench_n{n}{suffix}.json"))
 # other kernels of the round: raw metrics + per-function breakdown + tensor-core SASS evidence
 EXTRA = {"policy_tc": ("_ZN4orca20policy_mlp_tc_kernelENS_7MlpArgsE", "policy_mlp_tc_kernel"),
-         "obs": ("_ZN4orca14observe_kernelENS_7ObsArgsEi", "observe_kernel")}
+         "obs": ("_ZN4orca14observe_kernelENS_7ObsArgsEi", "observe_kernel"),
+         "grid": ("_ZN4orca16step_grid_kernelILi10ELb1ELi1EEEvNS_8StepArgsEPK6float2S4_PKiS6_PKNS_10GridParamsE",
+                  "step_grid_kernel")}
 for short, (mangled, nice) in EXTRA.items():
     rep2 = os.path.join(G, f"prof_{tag}_{short}.ncu-rep")
     if not os.path.exists(rep2):
