@@ -664,17 +664,13 @@ struct NearestKeys {
 #endif
 
 struct CandidateBuffer {
-  float4* base;  // slot r of this lane at base[r * stride]; .x = distSq, .y = id bits
+  float4* base;  // two entries per 16-byte line slot: entry r in half (r & 1) of base[(r >> 1) * stride]
   int stride;
-  int cap;
+  int cap;       // entries = 2 x line slots
   int cnt;
+  ORCA_HD float2* entry(int r) const { return reinterpret_cast<float2*>(&base[(r >> 1) * stride]) + (r & 1); }
   ORCA_HD void push(float d, int id) {
-    float4 e;
-    e.x = d;
-    e.y = bits_to_float(id);
-    e.z = 0.f;
-    e.w = 0.f;
-    base[cnt * stride] = e;
+    *entry(cnt) = v2(d, bits_to_float(id));  // (distSq, id bits)
     ++cnt;
   }
   template <class Insert>
@@ -682,7 +678,7 @@ struct CandidateBuffer {
     const int rounds = ORCA_WARP_MAX(mask, cnt);
     for (int r = 0; r < rounds; ++r) {
       if (r < cnt) {
-        const float4 e = base[r * stride];
+        const float2 e = *entry(r);
         insert(e.x, float_to_bits(e.y));
       }
     }

@@ -110,7 +110,7 @@ struct GridSource {
     CandidateBuffer buf;
     buf.base = scratch.base;
     buf.stride = scratch.stride;
-    buf.cap = scratch_slots;
+    buf.cap = 2 * scratch_slots;  // two (distSq, id) entries per 16-byte line slot
     buf.cnt = 0;
     auto insert = [&nk, &before](float d, int id) { nk.offer_ranked(d, id, before); };
     const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < gp.W ? cx + 1 : gp.W - 1;

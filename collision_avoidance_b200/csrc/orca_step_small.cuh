@@ -182,7 +182,7 @@ struct TileSource {
     CandidateBuffer buf;
     buf.base = scratch.base;
     buf.stride = scratch.stride;
-    buf.cap = scratch_slots;
+    buf.cap = 2 * scratch_slots;  // two (distSq, id) entries per 16-byte line slot
     buf.cnt = 0;
     if (cell_start != nullptr) {
       LowerIdFirst before;
