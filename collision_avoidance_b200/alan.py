@@ -49,7 +49,8 @@ class Collision_Avoidance_Sim:
     """Batch of ``num_envs`` ALAN worlds of ``numAgents`` agents each."""
 
     def __init__(self, numAgents: int = 50, scenario: str = "crowd", online_actions: Optional[Sequence] = None,
-                 visualize: bool = False, num_envs: int = 1, seed: int = 0, device="cuda:0"):
+                 visualize: bool = False, num_envs: int = 1, seed: int = 0, device="cuda:0",
+                 reference_rng: bool = False):
         if visualize:
             raise NotImplementedError("the Tk visualisation of the reference is out of scope (SURVEY section 2, #9)")
         # ORCA config, ALAN_true.py:15-20
@@ -70,6 +71,7 @@ class Collision_Avoidance_Sim:
         self.scenario = scenario
         self.num_envs = int(num_envs)
         self.seed = int(seed)
+        self.reference_rng = bool(reference_rng)   # world e == the reference after random.seed(seed + e)
         self.device = torch.device(device)
         self.max_step = int((10 / self.timeStep) * self.numAgents)
         self.visualize = False
@@ -79,7 +81,10 @@ class Collision_Avoidance_Sim:
 
     # ------------------------------------------------------------------ world
     def _init_world(self):
-        scn = scenarios.make(self.scenario, self.num_envs, self.numAgents, seed=self.seed + 7919 * self._episode)
+        kw = dict(reference_rng=True) if self.reference_rng else {}
+        if self.reference_rng and self.scenario == "circle":
+            kw["rotate"] = False
+        scn = scenarios.make(self.scenario, self.num_envs, self.numAgents, seed=self.seed + 7919 * self._episode, **kw)
         self.scn = scn
         self.envsize = scn.envsize
         dev = self.device

@@ -18,14 +18,18 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import _lib, scenarios
+from . import _lib, scenarios, spaces
 from .sim import BatchedRVOSimulator
 
 
 class Collision_Avoidance_Env:
     metadata = {"render.modes": []}
 
-    def __init__(self, numAgents: int = 10, num_envs: int = 1, seed: int = 0, device="cuda:0"):
+    def __init__(self, numAgents: int = 10, num_envs: int = 1, seed: int = 0, device="cuda:0",
+                 reference_rng: bool = False):
+        """``reference_rng``: world ``e`` draws its spawn positions from ``random.Random(seed + e)``
+        in the reference's call order, i.e. it is the world the reference builds (and re-draws at
+        every ``reset``) after ``random.seed(seed + e)``."""
         # constants, collision_avoidence_env.py:27-44
         self.timeStep = 1 / 60.
         self.neighborDist = 1.5
@@ -42,20 +46,25 @@ class Collision_Avoidance_Env:
         self.max_step = 1000
         self.reward_scale = 0.3          # :396
         self.done_x = 2.0                # :359
-        # "spaces" (:52-53): Box(-pi, pi, (1,)) and Box(-nd, nd, (laser_num*4,))
+        # spaces (:52-53): Box(-pi, pi, (1,)) and Box(-nd, nd, (laser_num*4,)), per agent
+        self.action_space, self.observation_space = spaces.env_spaces(self.neighborDist, self.laser_num)
         self.action_low, self.action_high, self.action_shape = -pi, pi, (1,)
         self.observation_low, self.observation_high = -self.neighborDist, self.neighborDist
         self.observation_shape = (self.laser_num * 4,)
         self.device = torch.device(device)
         self._rng = np.random.default_rng(seed)
         self._seed = seed
+        self._streams = scenarios.reference_streams(seed, self.num_envs) if reference_rng else None
         self._init_world()
         self.reset()
 
     # ------------------------------------------------------------------ world (:77-123)
     def _init_world(self):
         E, N = self.num_envs, self.numAgents
-        scn = scenarios.default_env(E, N, seed=int(self._rng.integers(0, 2 ** 31 - 1)))
+        if self._streams is not None:
+            scn = scenarios.default_env(E, N, reference_rng=self._streams)
+        else:
+            scn = scenarios.default_env(E, N, seed=int(self._rng.integers(0, 2 ** 31 - 1)))
         self.scn = scn
         dev = self.device
         self.sim = BatchedRVOSimulator(E, N, device=dev, **scn.params)
@@ -79,9 +88,17 @@ class Collision_Avoidance_Env:
         finished and the neighbor lists are NOT reset.  ``env_mask`` ([E] bool)
         restricts the reset to some worlds (vector-env use); default all."""
         E, N = self.num_envs, self.numAgents
-        x = self._rng.uniform(self.envsize * 0.5, self.envsize, size=(E, N))
-        y = self._rng.uniform(0, self.envsize, size=(E, N))
-        new_pos = torch.from_numpy(np.stack([x, y], -1).astype(np.float32)).to(self.device)
+        if self._streams is not None:
+            # only the selected worlds consume their stream, like separate reference envs would
+            sel = range(E) if env_mask is None else [e for e in range(E) if bool(env_mask[e])]
+            drawn = scenarios.default_env_reset_positions([self._streams[e] for e in sel], N, self.envsize)
+            full = self.sim.pos.cpu().numpy().copy()
+            full[list(sel)] = drawn
+            new_pos = torch.from_numpy(full).to(self.device)
+        else:
+            x = self._rng.uniform(self.envsize * 0.5, self.envsize, size=(E, N))
+            y = self._rng.uniform(0, self.envsize, size=(E, N))
+            new_pos = torch.from_numpy(np.stack([x, y], -1).astype(np.float32)).to(self.device)
         if env_mask is None:
             self.sim.pos.copy_(new_pos)
             self.env_step.zero_()
