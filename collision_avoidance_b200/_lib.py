@@ -21,7 +21,7 @@ ORCA_ERR_UNSUPPORTED = -3
 ORCA_ERR_STATE = -4
 
 POLICY_EXTERNAL, POLICY_GOAL, POLICY_RL, POLICY_ALAN = 0, 1, 2, 3
-DONE_NONE, DONE_GOAL_RADIUS, DONE_X_BELOW = 0, 1, 2
+DONE_NONE, DONE_GOAL_RADIUS, DONE_X_BELOW, DONE_GOAL_RADIUS_DEFERRED = 0, 1, 2, 3
 
 STAT_AGENT_STEPS, STAT_FINISHED, STAT_COLLISIONS, STAT_LP3_CALLS, STAT_OVERFLOW = 0, 1, 2, 3, 4
 STAT_SUM_ARRIVAL, STAT_SUM_ARRIVAL2, STAT_SUM_REWARD, STAT_COUNT = 5, 6, 7, 8
@@ -141,8 +141,8 @@ def load() -> ctypes.CDLL:
     for name in EXPORTED_SYMBOLS:
         if name not in ("orca_last_error", "orca_launch_count"):
             getattr(L, name).restype = i
-    if L.orca_abi_version() != 1:
-        raise OrcaLibraryError(f"ABI version mismatch: library reports {L.orca_abi_version()}, binding expects 1")
+    if L.orca_abi_version() != 2:
+        raise OrcaLibraryError(f"ABI version mismatch: library reports {L.orca_abi_version()}, binding expects 2")
     _lib = L
     return L
 

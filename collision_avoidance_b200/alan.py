@@ -156,8 +156,12 @@ class Collision_Avoidance_Sim:
                           env_done_cnt=self.env_done_cnt, steps=steps)
 
     def orca_step(self, steps: int = 1):
-        """ALAN_true.py:631-636 for every world (doStep, then goal-directed preferred velocity)."""
-        self.sim.env_step(policy=_lib.POLICY_GOAL, goal=self.goal, goal2=self.goal2, done_mode=_lib.DONE_GOAL_RADIUS,
+        """ALAN_true.py:631-636 for every world (doStep, then goal-directed preferred velocity).
+        The reference updates the preferred velocity BEFORE done_test swaps an arrived agent's
+        target (run_sim :116-120), so the step after an arrival still aims at the old goal:
+        DONE_GOAL_RADIUS_DEFERRED reproduces that (``agents_done`` holds 2 for that one step)."""
+        self.sim.env_step(policy=_lib.POLICY_GOAL, goal=self.goal, goal2=self.goal2,
+                          done_mode=_lib.DONE_GOAL_RADIUS_DEFERRED,
                           agent_done=self.agents_done, arrival_time=self.agents_time, env_step=self.env_step,
                           env_done_cnt=self.env_done_cnt, steps=steps)
 

@@ -95,6 +95,7 @@ struct OrcaSim {
   float2* d_pos = nullptr;
   float2* d_vel = nullptr;
   float2* d_aux = nullptr;
+  bool host_state_valid = false;  // d_pos / d_vel hold a state uploaded by an orca_step_host(upload_state = 1) call
   cudaStream_t host_streams[kHostChunksMax] = {};
   cudaEvent_t host_fork = nullptr;
   cudaEvent_t host_join[kHostChunksMax] = {};
@@ -433,7 +434,14 @@ int orca_env_step(OrcaSim* s, const OrcaEnvStepArgs* in, void* stream) {
     if (!(in->alan_temp > 0.f)) return fail(ORCA_ERR_INVALID, "alan_temp must be > 0");
     if (in->alan_actions_env_stride < 0 || (in->alan_actions_env_stride > 0 && in->alan_actions_env_stride < in->alan_num_actions))
       return fail(ORCA_ERR_INVALID, "alan_actions_env_stride must be 0 or >= alan_num_actions");
+    // the step counter drives the Philox counter AND the weight-window reset: without it every step
+    // would repeat step 0 (same draw, no reset) -- refuse instead of misbehaving silently
+    if (in->env_step_dev == nullptr) return fail(ORCA_ERR_INVALID, "ALAN policy needs env_step_dev");
   }
+  if (in->arrival_time_dev != nullptr && in->env_step_dev == nullptr)
+    return fail(ORCA_ERR_INVALID, "arrival_time_dev needs env_step_dev (arrival time = step * time_step)");
+  if (in->done_mode < ORCA_DONE_NONE || in->done_mode > ORCA_DONE_GOAL_RADIUS_DEFERRED)
+    return fail(ORCA_ERR_INVALID, "unknown done_mode %d", in->done_mode);
   if (in->done_mode != ORCA_DONE_NONE) {
     if (in->agent_done_dev == nullptr) return fail(ORCA_ERR_INVALID, "done_mode needs agent_done_dev");
     if (in->goal_dev == nullptr) return fail(ORCA_ERR_INVALID, "done_mode needs goal_dev");
@@ -571,9 +579,12 @@ int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* p
   if (policy != ORCA_POLICY_EXTERNAL && policy != ORCA_POLICY_GOAL)
     return fail(ORCA_ERR_INVALID, "orca_step_host supports the EXTERNAL and GOAL policies");
   if (steps < 1) return fail(ORCA_ERR_INVALID, "steps must be >= 1");
+  if (!upload_state && !s->host_state_valid)
+    return fail(ORCA_ERR_STATE, "orca_step_host(upload_state = 0) before any call uploaded the state");
   DeviceGuard guard(s->device);
   int rc = ensure_host_staging(s);
   if (rc != ORCA_OK) return rc;
+  if (upload_state) s->host_state_valid = true;
   // ---- direct path: the host buffers are pinned and mapped -------------------------------------
   // The step kernel itself reads the goals / preferred velocities from the caller's buffer and
   // writes the new positions and velocities into the caller's buffers (as well as into the

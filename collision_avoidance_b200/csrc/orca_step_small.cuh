@@ -24,7 +24,7 @@ namespace orca {
 constexpr int kMaxDevices = 64;  // size of the per-device "attribute already set" tables of the launchers
 
 enum : int { POLICY_EXTERNAL = 0, POLICY_GOAL = 1, POLICY_RL = 2, POLICY_ALAN = 3 };
-enum : int { DONE_NONE = 0, DONE_GOAL_RADIUS = 1, DONE_X_BELOW = 2 };
+enum : int { DONE_NONE = 0, DONE_GOAL_RADIUS = 1, DONE_X_BELOW = 2, DONE_GOAL_RADIUS_DEFERRED = 3 };
 enum : int {
   STAT_AGENT_STEPS = 0,
   STAT_FINISHED = 1,
@@ -256,6 +256,36 @@ ORCA_HD void stat_add_f64(unsigned long long* stats, int slot, double v) {
 #endif
   }
 }
+// One atomic per warp instead of one per thread: every live lane of the warp calls this together
+// (a converged point of the step), the lanes' values are summed with one REDUX instruction and the
+// first live lane issues the atomic -- and none at all when the warp's sum is zero.  With per-thread
+// atomics the LP3 / collision counters were up to 400,000 same-address atomics per launch.
+ORCA_HD void stat_add_u64_warp(unsigned long long* stats, int slot, unsigned v) {
+#if defined(__CUDA_ARCH__)
+  if (stats == nullptr) return;  // uniform over the launch
+  const unsigned m = __activemask();
+  const unsigned total = __reduce_add_sync(m, v);
+  if (total != 0u && (int)(threadIdx.x & 31u) == __ffs((int)m) - 1) atomicAdd(&stats[slot], (unsigned long long)total);
+#else
+  stat_add_u64(stats, slot, (unsigned long long)v);
+#endif
+}
+ORCA_HD void stat_add_f64_warp(unsigned long long* stats, int slot, float v) {
+#if defined(__CUDA_ARCH__)
+  if (stats == nullptr) return;
+  const unsigned m = __activemask();
+  double total = (double)v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(m, total, o);
+    // lanes outside m return their own value for the partner; only add partners that are live
+    if ((m >> ((threadIdx.x & 31u) ^ o)) & 1u) total += other;
+  }
+  if ((int)(threadIdx.x & 31u) == __ffs((int)m) - 1) atomicAdd(reinterpret_cast<double*>(&stats[slot]), total);
+#else
+  stat_add_f64(stats, slot, (double)v);
+#endif
+}
 ORCA_HD void counter_inc(int* c) {
 #if defined(__CUDA_ARCH__)
   atomicAdd(c, 1);
@@ -474,7 +504,8 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
 template <int POLICY>
 ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const int g, const int estep,
                         const AgentCarry& c) {
-  if (c.fail < c.n) stat_add_u64(a.stats, STAT_LP3_CALLS, 1ull);
+  stat_add_u64_warp(a.stats, STAT_AGENT_STEPS, 1u);
+  stat_add_u64_warp(a.stats, STAT_LP3_CALLS, c.fail < c.n ? 1u : 0u);
 
   // ---------------- integrate (Agent::update) ----------------
   const float2 v = c.nv;
@@ -496,6 +527,7 @@ ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const in
     else
       R = a.alan_gamma * r_goal + (1.f - a.alan_gamma) * r_polite;
     if (a.reward != nullptr) a.reward[g] = R;
+    stat_add_f64_warp(a.stats, STAT_SUM_REWARD, R);
     if (POLICY == POLICY_ALAN) {
       float* wrow = a.alan_w + (size_t)g * a.A;
       // every per-action timer advances in lock step, so the 2 s window expires for all of
@@ -508,20 +540,29 @@ ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const in
   }
 
   // ---------------- done test ----------------
+  // DONE_GOAL_RADIUS_DEFERRED is the order of run_sim(mode=0) (ALAN_true.py:116-120,631-633): there
+  // the preferred velocity of the NEXT doStep is computed (update_pref_vel) before done_test swaps
+  // the target, so the step after an arrival still aims at the old goal.  The flag value 2 =
+  // "arrived in the previous step, goal swap pending" carries that over one step.
   if (a.done_mode != DONE_NONE) {
-    if (a.done[g] == 0) {
+    const uint8_t flag = a.done[g];
+    if (flag == 2) {
+      a.done[g] = 1;
+      if (a.goal2 != nullptr) a.goal[g] = a.goal2[g];
+    } else if (flag == 0) {
       bool hit;
-      if (a.done_mode == DONE_GOAL_RADIUS) {
+      if (a.done_mode != DONE_X_BELOW) {
         const float2 d = sub(p, a.goal[g]);
         hit = sqrtf(abs_sq(d)) < 2.f * a.radius;
       } else {
         hit = p.x < a.done_x;
       }
       if (hit) {
-        a.done[g] = 1;
+        const bool defer = a.done_mode == DONE_GOAL_RADIUS_DEFERRED;
+        a.done[g] = defer ? 2 : 1;
         const float t_arr = (float)(estep + 1) * a.dt;
         if (a.arrival != nullptr) a.arrival[g] = t_arr;
-        if (a.goal2 != nullptr) a.goal[g] = a.goal2[g];
+        if (a.goal2 != nullptr && !defer) a.goal[g] = a.goal2[g];
         if (a.env_done_cnt != nullptr) counter_inc(&a.env_done_cnt[env]);
         stat_add_u64(a.stats, STAT_FINISHED, 1ull);
         stat_add_f64(a.stats, STAT_SUM_ARRIVAL, (double)t_arr);
@@ -530,8 +571,8 @@ ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const in
     }
   }
   if (a.env_step != nullptr && la == 0 && !a.grid_path) a.env_step[env] = estep + 1;
-  stat_add_u64(a.stats, STAT_COLLISIONS, (unsigned long long)c.collisions);
-  stat_add_u64(a.stats, STAT_OVERFLOW, c.overflow ? 1ull : 0ull);
+  stat_add_u64_warp(a.stats, STAT_COLLISIONS, c.collisions);
+  stat_add_u64_warp(a.stats, STAT_OVERFLOW, c.overflow ? 1u : 0u);
 }
 
 // Front + LP3 + back for one agent, no work redistribution (host emulation; reference order).

@@ -4,7 +4,7 @@ The reference shells talk to RVO2 through 16 methods with Python tuples in and o
 (collision_avoidence_env.py:62-68,123-148,154-157,237-252,283-312,385,479 and
 ALAN_true.py:22-28,461-479,490,553,598-613).  This class offers exactly those, so
 ``sys.modules['rvo2'] = collision_avoidance_b200.rvo2_compat`` lets the reference's shell logic
-run unmodified against the CUDA path (tests/test_gpu_compat.py does that).  It is a
+run unmodified against the CUDA path (tests/test_gpu_compat.py replays the recorded call trace of the unmodified shells against it).  It is a
 compatibility shim, not the fast path: every ``doStep`` is one kernel launch for one world plus
 host<->device mirrors; throughput comes from ``BatchedRVOSimulator`` / ``envs`` / ``alan``.
 

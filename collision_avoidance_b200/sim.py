@@ -291,6 +291,7 @@ class BatchedRVOSimulator:
         s = self.stats.cpu()
         f = s.view(torch.float64)
         return {
+            "agent_steps": int(s[_lib.STAT_AGENT_STEPS]), "sum_reward": float(f[_lib.STAT_SUM_REWARD]),
             "finished": int(s[_lib.STAT_FINISHED]), "collisions": int(s[_lib.STAT_COLLISIONS]),
             "lp3_calls": int(s[_lib.STAT_LP3_CALLS]), "overflow": int(s[_lib.STAT_OVERFLOW]),
             "sum_arrival": float(f[_lib.STAT_SUM_ARRIVAL]), "sum_arrival2": float(f[_lib.STAT_SUM_ARRIVAL2]),

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ORCA_B200_ABI_VERSION 1
+#define ORCA_B200_ABI_VERSION 2
 
 typedef enum OrcaStatus {
   ORCA_OK = 0,
@@ -66,19 +66,23 @@ typedef enum OrcaPolicy {
 typedef enum OrcaDoneMode {
   ORCA_DONE_NONE = 0,
   ORCA_DONE_GOAL_RADIUS = 1, /* |pos - goal| < 2*radius -> record time, goal <- goal2 : ALAN_true.py:547-566 */
-  ORCA_DONE_X_BELOW = 2      /* pos.x < x_threshold    -> goal <- goal2              : collision_avoidence_env.py:352-365 */
+  ORCA_DONE_X_BELOW = 2,     /* pos.x < x_threshold    -> goal <- goal2              : collision_avoidence_env.py:352-365 */
+  /* GOAL_RADIUS in the order of run_sim(mode=0) (ALAN_true.py:116-120,631-633): orca_step computes the
+   * preferred velocity of the NEXT doStep before done_test swaps the target, so the step right after an
+   * arrival still aims at the old goal.  agent_done holds 2 for that one step ("swap pending"), then 1. */
+  ORCA_DONE_GOAL_RADIUS_DEFERRED = 3
 } OrcaDoneMode;
 
 /* Slots of the device statistics vector (uint64 counters / float64 sums, 8 bytes each). */
 enum {
-  ORCA_STAT_AGENT_STEPS = 0,  /* u64 */
+  ORCA_STAT_AGENT_STEPS = 0,  /* u64: agents advanced by one step */
   ORCA_STAT_FINISHED = 1,     /* u64: agents that reached their goal */
   ORCA_STAT_COLLISIONS = 2,   /* u64: (agent, neighbor) pairs with distSq <= (2r)^2 (RVO2's collision branch) */
   ORCA_STAT_LP3_CALLS = 3,    /* u64: agents whose LP2 was infeasible */
   ORCA_STAT_OVERFLOW = 4,     /* u64: agents that exceeded the obstacle-neighbor / line capacity */
   ORCA_STAT_SUM_ARRIVAL = 5,  /* f64: sum of arrival times  (TTime, ALAN_true.py:125-131) */
   ORCA_STAT_SUM_ARRIVAL2 = 6, /* f64: sum of squared arrival times */
-  ORCA_STAT_SUM_REWARD = 7,   /* f64 */
+  ORCA_STAT_SUM_REWARD = 7,   /* f64: sum of the per-agent rewards (RL and ALAN policies) */
   ORCA_STAT_COUNT = 8
 };
 
@@ -123,7 +127,9 @@ typedef struct OrcaEnvStepArgs {
   float* reward_dev;         /* [E*N] optional */
   uint8_t* agent_done_dev;   /* [E*N] in/out, required when done_mode != NONE */
   float* arrival_time_dev;   /* [E*N] in/out optional: agents_time (ALAN :559) */
-  int32_t* env_step_dev;     /* [E] in/out step counter (step_count, ALAN :117, env :408) */
+  int32_t* env_step_dev;     /* [E] in/out step counter (step_count, ALAN :117, env :408).  REQUIRED with
+                              * ORCA_POLICY_ALAN (Philox counter, weight-window reset) and whenever
+                              * arrival_time_dev is given (arrival time = step * dt): ORCA_ERR_INVALID otherwise */
   int32_t* env_done_cnt_dev; /* [E] in/out number of done agents; env done <=> == N */
 
   /* neighbor lists of THIS step (pre-update positions), optional:

@@ -721,6 +721,15 @@ void rvo_get_agent_orca_line(void* h, int i, int j, float* out) {
 }
 
 // ---- bulk accessors (test convenience; same state, arrays of [n][2]) ----------
+// addAgent(pos) with the simulator's default parameters for n agents; vel = initial velocities
+int rvo_add_agents(void* h, const float* pos, const float* vel, int n) {
+  Sim* s = S(h);
+  int last = -1;
+  for (int i = 0; i < n; ++i)
+    last = s->add_agent(V2(pos[2 * i], pos[2 * i + 1]), s->d_nd, s->d_k, s->d_th, s->d_tho, s->d_radius, s->d_vmax,
+                        V2(vel[2 * i], vel[2 * i + 1]));
+  return last;
+}
 void rvo_get_positions(void* h, float* out) {
   Sim* s = S(h);
   for (size_t i = 0; i < s->agents.size(); ++i) {

@@ -46,6 +46,7 @@ def lib() -> ctypes.CDLL:
         "rvo_destroy": (None, [p]),
         "rvo_add_agent": (i, [p, f, f, f, i, f, f, f, f, f, f]),
         "rvo_add_agent_default": (i, [p, f, f]),
+        "rvo_add_agents": (i, [p, fp, fp, i]),
         "rvo_add_obstacle": (i, [p, fp, i]),
         "rvo_process_obstacles": (None, [p]),
         "rvo_do_step": (None, [p]),
@@ -190,6 +191,12 @@ class PyRVOSimulator:
         return float(self._L.rvo_global_time(self._h))
 
     # -- oracle-only bulk helpers (float32 arrays [n,2]) --------------------
+    def add_agents(self, pos, vel):
+        """addAgent(pos) with the constructor's defaults for every row; ``vel`` = initial velocities."""
+        pos = np.ascontiguousarray(pos, np.float32)
+        vel = np.ascontiguousarray(vel, np.float32)
+        return self._L.rvo_add_agents(self._h, _fptr(pos), _fptr(vel), int(pos.shape[0]))
+
     def positions(self):
         out = np.empty((self.getNumAgents(), 2), np.float32)
         self._L.rvo_get_positions(self._h, _fptr(out))

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_struct_layout(lib):
     from collision_avoidance_b200 import _lib
-    assert lib.orca_abi_version() == 1
+    assert lib.orca_abi_version() == 2
     assert ctypes.sizeof(_lib.OrcaParams) == 28
     # the library validates struct_size; the Python mirror must be 8-byte aligned and match C
     assert ctypes.sizeof(_lib.OrcaEnvStepArgs) % 8 == 0

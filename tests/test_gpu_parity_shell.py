@@ -260,3 +260,68 @@ def test_mcmc_trainer_runs_and_never_worsens_the_best():
     assert min(tr.eval_opt) <= first
     assert all(abs(a[0] ** 2 + a[1] ** 2 - 1) < 1e-9 for a in best)
     assert tr.temp < 0.9     # annealing cools down (the reference heats up; see module docstring)
+
+
+def test_per_world_action_tables_match_shell_with_own_sets():
+    """Row f1 against the oracle: a batch whose worlds carry DIFFERENT action sets (sizes 3, 9, 8,
+    2 -- the reference's own .act tables) steps like separate shells constructed with
+    ``online_actions=sets[e]`` (ALAN_true.py:41-44, Train_ALAN_action_space.py:58), from shared
+    states, under shared uniforms."""
+    import json
+    import os
+    torch = _torch()
+    from collision_avoidance_b200 import alan
+    from oracle.shell_oracle import AlanShellOracle
+    with open(os.path.join(os.path.dirname(__file__), "golden", "act_tables.json")) as f:
+        tabs = json.load(f)
+    sets = [[tuple(a) for a in tabs["circle"]], [tuple(a) for a in tabs["crowd"]], list(alan.DEFAULT_ONLINE_ACTIONS),
+            [tuple(a) for a in tabs["deadlock"]]]
+    E, N, steps = len(sets), 14, 250
+    gpu = alan.Collision_Avoidance_Sim(numAgents=N, scenario="crowd", online_actions=sets, num_envs=E, seed=17)
+    shells = [AlanShellOracle(gpu.scn, e, online_actions=sets[e]) for e in range(E)]
+    A = gpu.action_weights.shape[-1]
+    rng = np.random.default_rng(6)
+    worst_state = worst_w = 0.0
+    mismatch = 0
+    for t in range(steps):
+        _sync_alan_padded(gpu, shells, A)
+        u = rng.random((E, N)).astype(np.float32)
+        for e, sh in enumerate(shells):
+            sh.online_step(u[e])
+            sh.step_count += 1
+            sh.done_test()
+        gpu.online_step(uniforms=torch.from_numpy(u).cuda())
+        act_o = np.array([sh.last["action_ids"] for sh in shells])
+        same = gpu.action_ids.cpu().numpy() == act_o
+        mismatch += int((~same).sum())
+        ov = np.stack([s.sim.velocities() for s in shells])
+        worst_state = max(worst_state, float(np.abs(gpu.sim.vel.cpu().numpy() - ov)[same].max()))
+        w_g = gpu.action_weights.cpu().numpy()
+        for e, sh in enumerate(shells):
+            n = len(sets[e])
+            worst_w = max(worst_w, float(np.abs(w_g[e, :, :n] - np.array(sh.action_weights))[same[e]].max()))
+            assert int(gpu.action_ids[e].max()) < n
+    print(f"per-world tables: state={worst_state:.3g} weights={worst_w:.3g} action mismatches={mismatch}/{steps * E * N}")
+    assert worst_state <= TOL_STATE and worst_w <= TOL_REWARD and mismatch <= 2
+
+
+def _sync_alan_padded(gpu, shells, A):
+    torch = _torch()
+    _sync_alan_state(gpu, shells)
+    w = np.zeros((len(shells), shells[0].N, A), np.float32)
+    for e, s in enumerate(shells):
+        aw = np.array(s.action_weights, np.float32)
+        w[e, :, :aw.shape[1]] = aw
+    gpu.action_weights.copy_(torch.from_numpy(w))
+
+
+def _sync_alan_state(gpu, shells):
+    torch = _torch()
+    gpu.sim.pos.copy_(torch.from_numpy(np.stack([s.sim.positions() for s in shells])))
+    gpu.sim.vel.copy_(torch.from_numpy(np.stack([s.sim.velocities() for s in shells])))
+    gpu.goal.copy_(torch.from_numpy(np.array([[t[0] for t in s.targets] for s in shells], np.float32)))
+    done = np.array([s.agents_done for s in shells], np.uint8)
+    gpu.agents_done.copy_(torch.from_numpy(done))
+    gpu.env_done_cnt.copy_(torch.from_numpy(done.sum(1).astype(np.int32)))
+    gpu.env_step.copy_(torch.from_numpy(np.array([s.step_count for s in shells], np.int32)))
+    gpu.agents_time.copy_(torch.from_numpy(np.array([s.agents_time for s in shells], np.float32)))

@@ -294,3 +294,81 @@ def test_full_size_batches_are_env_independent(name, small_envs, copies, agents,
     assert np.array_equal(bv, np.broadcast_to(sv, bv.shape))
     st_s, st_b = small.read_stats(), big.read_stats()
     assert st_b["collisions"] == copies * st_s["collisions"] and st_b["lp3_calls"] == copies * st_s["lp3_calls"]
+
+
+def test_cfg4_world_256_agents_with_blocks_matches_oracle_for_50_steps():
+    """BASELINE configs[3]'s world shape at full agent count: 256 agents + wall + 4 blocks,
+    50 oracle-synchronised steps (neighbor lists, obstacle lists, bit-exact velocities)."""
+    from collision_avoidance_b200 import scenarios
+    scn = scenarios.crowd(2, 256, seed=41, blocks=4)
+    worst, exact = _run_case(scn, steps=50)
+    assert exact == 1.0, (worst, exact)
+
+
+def test_million_agent_world_one_oracle_step():
+    """BASELINE configs[4] at full size against the oracle itself: one doStep of the 1,000,000
+    agent world (uniform grid on the GPU, kd-tree in the oracle), velocities and positions within
+    1e-4 and -- wherever the ordered neighbor lists agree -- bit-identical."""
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    from collision_avoidance_b200.sim import BatchedRVOSimulator
+    from oracle import rvo2_oracle
+    N = 1_000_000
+    scn = scenarios.crowd(1, N, seed=15)
+    P = scn.params
+    sim = BatchedRVOSimulator(1, N, device="cuda:0", **P)
+    sim.set_obstacles(scn.obstacles)
+    goal = torch.from_numpy(scn.goal).cuda()
+    sim.pos.copy_(torch.from_numpy(scn.pos))
+    sim.vel.copy_(torch.from_numpy(scn.vel))
+    for _ in range(40):            # spread the uniformly random start (heavy overlaps) into a settled crowd
+        sim.env_step(policy=_lib.POLICY_GOAL, goal=goal)
+    pos, vel = sim.pos.cpu().numpy()[0], sim.vel.cpu().numpy()[0]
+    pref = goal_pref(pos, scn.goal[0]).astype(np.float32)
+    o = rvo2_oracle.PyRVOSimulator(P["timeStep"], P["neighborDist"], P["maxNeighbors"], P["timeHorizon"],
+                                   P["timeHorizonObst"], P["radius"], P["maxSpeed"])
+    o.add_agents(pos, vel)
+    for poly in scn.obstacles:
+        o.addObstacle([tuple(map(float, v)) for v in poly])
+    o.processObstacles()
+    o.set_pref_velocities(pref)
+    o.doStep()
+    sim.pref.copy_(torch.from_numpy(pref[None]))
+    sim.doStep()
+    gv, gp = sim.vel.cpu().numpy()[0], sim.pos.cpu().numpy()[0]
+    ov, op = o.velocities(), o.positions()
+    dv = np.abs(gv - ov).max(1)
+    exact = float((dv == 0).mean())
+    print(f"1M agents: worst dv={dv.max():.3g} worst dp={np.abs(gp - op).max():.3g} bit-exact agents={exact:.6f}")
+    assert dv.max() <= TOL and np.abs(gp - op).max() <= TOL
+    assert exact > 0.999          # the rest: ordered lists differing in bit-equal distances (tie exemption)
+
+
+def test_collision_statistic_equals_the_oracle_count():
+    """ORCA_STAT_COLLISIONS counts (agent, neighbor) pairs in RVO2's collision branch,
+    distSq <= (r_i + r_j)^2, over the neighbor lists of the step -- compared with the same count
+    taken from the oracle's lists (overlapping random crowds, tile and grid paths)."""
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    for scn in (scenarios.crowd(6, 64, seed=51), scenarios.crowd(1, 600, seed=52)):
+        sims = oracle_sims(scn)
+        gpu = _gpu_sim(scn)
+        cr_sq = np.float32(2 * scn.params["radius"]) ** 2
+        total_o = 0
+        for t in range(12):
+            pos = np.stack([s.positions() for s in sims])
+            vel = np.stack([s.velocities() for s in sims])
+            pref = goal_pref(pos, scn.goal).astype(np.float32)
+            for e, s in enumerate(sims):
+                s.set_pref_velocities(pref[e])
+                s.doStep()
+                for i in range(scn.agents_per_env):
+                    total_o += sum(1 for _, d in s.agent_neighbors(i) if np.float32(d) <= cr_sq)
+            gpu.pos.copy_(torch.from_numpy(pos))
+            gpu.vel.copy_(torch.from_numpy(vel))
+            gpu.pref.copy_(torch.from_numpy(pref))
+            gpu.env_step(policy=_lib.POLICY_EXTERNAL)
+        st = gpu.read_stats()
+        assert total_o > 50
+        assert st["collisions"] == total_o, (scn.name, st, total_o)
+        assert st["agent_steps"] == 12 * scn.num_envs * scn.agents_per_env
