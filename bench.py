@@ -1,20 +1,32 @@
 #!/usr/bin/env python
 """Headline benchmark: ORCA agent-steps/sec (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2|cfg3|cfg4|cfg5]
 
-Workload at every N: BASELINE.json configs[1] per GPU -- circle-crossing, 16 agents/env x
-65,536 envs, ORCA policy (doStep + goal-directed preferred velocity + done test, i.e. the
-reference's run_sim(mode=0) loop, ALAN_true.py:106-131,631-636,547-566).  Env instances are
-independent, so N GPUs each own 65,536 envs (weak scaling, no data-path collective); episode
-statistics are all-reduced once after the timed region.
+Workloads = BASELINE.json configs, one GPU's share each (env instances are independent, so N GPUs
+each own one share: weak scaling, no data-path collective; episode statistics are all-reduced
+once after the timed region):
+  cfg2 (default, configs[1])  circle-crossing 16 agents x 65,536 envs, ORCA policy = the reference's
+                              run_sim(mode=0) loop: doStep + goal-directed preferred velocity + done
+                              test (ALAN_true.py:106-131,631-636,547-566)
+  cfg3 (configs[2])           circle 32 agents x 32,768 envs per GPU (262,144 over 8), ALAN online
+                              action selection, 8 candidate actions (ALAN_true.py:569-628)
+  cfg4 (configs[3])           dense crowd 256 agents + wall + 4 obstacle blocks x 2,048 envs per GPU
+  cfg5 (configs[4])           one world of 1,000,000 agents, uniform-grid neighbor search (1 GPU; N
+                              ranks run N replicas)
 
-A "step" is one fused environment step over every env of the rank (one kernel launch).
-  value      device-timed throughput, state resident in HBM (CUDA events around each launch,
-             L2 flushed between launches)
-  e2e        same metric through the host-buffer C-ABI call (orca_step_host): goals go
-             host->device and positions+velocities come device->host inside the timed region
-  roofline   algorithmic HBM bytes / kernel time vs. the measured copy bandwidth
+A "step" is one fused environment step over every env of the rank.  The cost of a step depends
+on the phase of the episode (for cfg2: 184 us in the first steps, ~270 us when the ring meets in
+the middle, less again once it has dissolved), so the timed window does not start at the reset
+state: the state is first advanced, untimed, to episode step `--episode-step` (default per
+config: the expensive mid-episode phase), then W warm-up steps, then exactly K timed steps.
+`ms_per_step_by_phase` / `episode_mean_ms_per_step` report the whole profile next to it.
+
+  value         device-timed throughput, state resident in HBM (CUDA events around each launch,
+                L2 flushed between launches), max over ranks
+  e2e           same metric through the host-buffer C-ABI call (orca_step_host): inputs go
+                host->device and the new state comes device->host inside the timed region
+  roofline      algorithmic HBM bytes / kernel time vs. the measured copy bandwidth
   cpu_baseline  the CPU oracle (restatement of RVO2, oracle/) on this box's host cores
 """
 from __future__ import annotations
@@ -22,7 +34,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -32,13 +43,26 @@ sys.path.insert(0, ROOT)
 
 METRIC = "orca_agent_steps_per_sec"
 UNIT = "agent-steps/s"
-WORKLOAD = "circle-crossing 16 agents/env x 65,536 envs, ORCA policy, per B200"
-ENVS_PER_GPU = 65536
-AGENTS = 16
-# algorithmic HBM bytes per agent-step of the fused step (DESIGN.md "Roofline"):
-# read pos 8 + vel 8 + goal 8 + done flag 1, write pos 8 + vel 8
-BYTES_PER_AGENT_STEP = 41
 SEED = 1234
+
+# name -> workload description.  bytes = algorithmic HBM bytes per agent-step (DESIGN.md section 5,
+# SURVEY 8d); episode_step = where the timed window starts (see module docstring)
+CONFIGS = {
+    "cfg2": dict(workload="circle-crossing 16 agents/env x 65,536 envs, ORCA policy, per B200", scenario="circle",
+                 envs=65536, agents=16, policy="orca_step + done_test", bytes=41, kernel="step_small_kernel<10,GOAL>",
+                 episode_step=130),
+    "cfg3": dict(workload="circle 32 agents/env x 32,768 envs per B200 (262,144 over 8), ALAN online action selection, "
+                          "8 candidate actions", scenario="circle", envs=32768, agents=32, policy="online_step (ALAN) + done_test",
+                 bytes=82, kernel="step_small_kernel<10,ALAN>", episode_step=130),
+    "cfg4": dict(workload="dense crowd 256 agents/env + wall + 4 obstacle blocks x 2,048 envs per B200 (16,384 over 8), "
+                          "ORCA policy", scenario="crowd_blocks", envs=2048, agents=256, policy="orca_step + done_test",
+                 bytes=48, kernel="step_small_kernel<10,GOAL> (in-block grid)", episode_step=60),
+    "cfg5": dict(workload="single-env crowd of 1,000,000 agents, maxNeighbors 10, uniform-grid neighbor search, 1 B200",
+                 scenario="crowd", envs=1, agents=1_000_000, policy="orca_step + done_test", bytes=150,
+                 kernel="grid pipeline + step_grid_kernel<10,GOAL>", episode_step=60),
+}
+PHASE_STEPS = {"cfg2": (10, 60, 130, 250, 500, 900), "cfg3": (10, 60, 130, 250, 500, 900), "cfg4": (10, 60, 150, 400),
+               "cfg5": (10, 60, 150)}
 
 
 def _peaks():
@@ -52,30 +76,20 @@ def _peaks():
 _RESULT_OUT = sys.stdout  # replaced in main() by a private duplicate of the real stdout
 
 
-def _traffic():
-    """dram bytes per launch of the step kernel from the committed ncu --set full capture."""
-    path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return json.load(f).get("step_small_kernel_dram_bytes_per_launch")
-    return None
-
-
-def _issue_profile():
-    """What actually bounds the step kernel (same ncu capture): issue-slot use, warp-instructions
-    per launch and live lanes per instruction.  Reported next to the HBM roofline, which this
-    kernel cannot approach."""
+def _static_profile(cfg_name):
+    """ncu figures of the dominant kernel from the COMMITTED capture (profiles/traffic.json): they
+    are not measured in this run and say which capture / episode step they come from."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
-        return None
+        return None, None
     with open(path) as f:
-        t = json.load(f)
-    if "step_small_kernel_issue_active_pct" not in t:
-        return None
-    return {"issue_slots_busy_frac": t["step_small_kernel_issue_active_pct"] / 100.0,
-            "warp_instructions_per_launch": t["step_small_kernel_warp_instructions_per_launch"],
-            "active_lanes_per_instruction": t["step_small_kernel_active_lanes_per_instruction"],
-            "source": "profiles/r01_step_small_ncu_raw.csv (ncu --set full, bench step ~100)"}
+        t = json.load(f).get(cfg_name)
+    if not t:
+        return None, None
+    prof = {k: t[k] for k in ("issue_slots_busy_frac", "warp_instructions_per_launch", "active_lanes_per_instruction")
+            if k in t}
+    prof.update(static=True, source=t.get("source"), episode_step=t.get("episode_step"))
+    return t.get("dram_bytes_per_launch"), prof
 
 
 class ClockSampler:
@@ -145,47 +159,63 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------
-def cpu_baseline(steps: int, warmup: int, target_seconds: float = 12.0, threads: int | None = None):
-    """Times the CPU oracle (the restatement of RVO2 the reference calls into) on the same
-    scenario and the same step window as the GPU run, one worker thread per host core.
-    Bounded sample: fewer envs, sized for ~target_seconds of CPU work."""
+def _scenario(cfg, envs, seed):
     from collision_avoidance_b200 import scenarios
+    if cfg["scenario"] == "crowd_blocks":
+        return scenarios.crowd(envs, cfg["agents"], seed=seed, blocks=4)
+    return scenarios.make(cfg["scenario"], envs, cfg["agents"], seed=seed)
+
+
+def _config_dict(cfg_name, cfg, args):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": cfg["workload"], "name": cfg_name, "envs_per_gpu": cfg["envs"], "agents_per_env": cfg["agents"],
+            "policy": cfg["policy"], "episode_window": [args.episode_step + args.warmup, args.episode_step + args.warmup + args.steps]}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_orca_throughput(cfg, envs, episode_step, warmup, steps, threads):
+    """The CPU oracle (C++ restatement of RVO2 behind the reference's shell loop: doStep + float64
+    goal-directed preferred velocity) on `envs` envs of the workload, `threads` host threads, over
+    the same episode window as the GPU arm.  Returns (agent-steps/s, seconds timed)."""
     from oracle import rvo2_oracle
     from oracle.helpers import oracle_sims
-    threads = threads or (os.cpu_count() or 1)
-    # calibrate on a small batch over the same window, then size the sample
-    cal_envs = 4 * threads
-    scn = scenarios.circle(cal_envs, AGENTS, seed=SEED)
+    scn = _scenario(cfg, envs, SEED)
     sims = oracle_sims(scn)
     goals = scn.goal.astype("float64")
-    t0 = time.perf_counter()
-    rvo2_oracle.batch_orca_steps(sims, goals, warmup + steps, threads)
-    cal = time.perf_counter() - t0
-    envs = int(max(cal_envs, min(65536, cal_envs * target_seconds / max(cal, 1e-6))))
-    envs -= envs % threads
-    scn = scenarios.circle(envs, AGENTS, seed=SEED)
-    sims = oracle_sims(scn)
-    goals = scn.goal.astype("float64")
-    rvo2_oracle.batch_orca_steps(sims, goals, warmup, threads)
+    if episode_step + warmup > 0:
+        rvo2_oracle.batch_orca_steps(sims, goals, episode_step + warmup, threads)
     t0 = time.perf_counter()
     rvo2_oracle.batch_orca_steps(sims, goals, steps, threads)
     dt = time.perf_counter() - t0
-    return {
-        "value": envs * AGENTS * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-        "sample": f"{envs} envs x {AGENTS} agents x {steps} steps after {warmup} warm-up steps of the same circle "
-                  f"scenario (C++ oracle: kd-tree + ORCA + LP, float64 pref update), {dt:.1f} s wall",
-    }
+    return envs * cfg["agents"] * steps / dt, dt
 
 
-def cpu_python_driver_baseline(steps: int = 30, envs: int = 8):
+def cpu_baseline(cfg, args, target_seconds: float = 15.0, threads: int | None = None):
+    """Bounded sample for the in-line `cpu_baseline` object of the GPU arm: as many envs of the
+    workload as ~target_seconds of host work cover (fast-forward included)."""
+    threads = min(threads or (os.cpu_count() or 1), cfg["envs"])
+    total_steps = args.episode_step + args.warmup + args.steps
+    # calibrate on a few envs over a short window
+    cal_envs = max(1, min(cfg["envs"], 2 * threads))
+    v, _ = cpu_orca_throughput(cfg, cal_envs, 0, 2, 8, threads)
+    envs = int(target_seconds * v / (cfg["agents"] * total_steps))
+    envs = max(1 if cfg["envs"] == 1 else threads, min(cfg["envs"], envs))
+    value, dt = cpu_orca_throughput(cfg, envs, args.episode_step, args.warmup, args.steps, threads)
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{envs} of {cfg['envs']} envs x {cfg['agents']} agents x {args.steps} steps of the same episode window "
+                      f"(steps {args.episode_step + args.warmup}..{args.episode_step + args.warmup + args.steps}), C++ oracle: kd-tree + ORCA + LP, "
+                      f"float64 preferred-velocity update, {dt:.2f} s timed"}
+
+
+def cpu_python_driver_baseline(cfg, steps: int = 30, envs: int = 8):
     """The reference's own call pattern on one core: per agent setAgentPrefVelocity, one doStep,
     per agent getAgentPosition/getAgentVelocity, all through Python (collision_avoidence_env.py
     :371-400), with the oracle standing in for rvo2.  This is what "Python-RVO2 as the reference
     uses it" costs; reported next to the C++-driver figure."""
     from collision_avoidance_b200 import scenarios
     from oracle.shell_oracle import AlanShellOracle
-    scn = scenarios.circle(envs, AGENTS, seed=SEED)
+    n = min(cfg["agents"], 64)
+    scn = scenarios.circle(envs, n, seed=SEED)
     shells = [AlanShellOracle(scn, e) for e in range(envs)]
     for sh in shells:
         sh.orca_step()
@@ -196,37 +226,36 @@ def cpu_python_driver_baseline(steps: int = 30, envs: int = 8):
             sh.step_count += 1
             sh.done_test()
     dt = time.perf_counter() - t0
-    return {"value": envs * AGENTS * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{envs} envs x {AGENTS} agents x {steps} steps, Python per-agent call pattern over the oracle"}
+    return {"value": envs * n * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{envs} envs x {n} agents x {steps} steps, Python per-agent call pattern over the oracle"}
 
 
-def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  rvo2
-    (Python-RVO2) is not available offline, so this times the oracle port of it (oracle/)
-    with all host threads on the same config; each step is a bounded sample of the workload."""
+def run_reference(args, cfg_name, cfg):
+    """--impl reference: the reference's own CPU implementation of the path.  rvo2 (Python-RVO2)
+    is not available offline, so this times the oracle port of it (oracle/) with all host threads
+    on the SAME config and episode window; each step covers the full per-GPU batch for cfg2 and a
+    bounded sample of it where the full batch would not finish within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from collision_avoidance_b200 import scenarios
-    from oracle import rvo2_oracle
-    from oracle.helpers import oracle_sims
-    threads = os.cpu_count() or 1
-    envs = 2048
-    scn = scenarios.circle(envs, AGENTS, seed=SEED)
-    sims = oracle_sims(scn)
-    goals = scn.goal.astype("float64")
-    rvo2_oracle.batch_orca_steps(sims, goals, args.warmup, threads)
-    t0 = time.perf_counter()
-    rvo2_oracle.batch_orca_steps(sims, goals, args.steps, threads)
-    dt = time.perf_counter() - t0
-    value = envs * AGENTS * args.steps / dt
-    sample = f"{envs} envs x {AGENTS} agents per step (bounded sample of the 65,536-env workload), {threads} threads"
+    threads = min(os.cpu_count() or 1, cfg["envs"])   # the oracle driver parallelises over envs
+    total_steps = args.episode_step + args.warmup + args.steps
+    # full batch when it costs < ~90 s of host work at ~3e6 agent-steps/s/thread, else a bounded sample
+    budget = 90.0 * 3.0e6 * threads
+    envs = cfg["envs"]
+    if cfg["envs"] * cfg["agents"] * total_steps > budget and cfg["envs"] > 1:
+        envs = max(threads, int(budget / (cfg["agents"] * total_steps)))
+    value, dt = cpu_orca_throughput(cfg, envs, args.episode_step, args.warmup, args.steps, threads)
+    note = "ORCA policy" if "ALAN" not in cfg["policy"] else \
+        "doStep + goal-directed preferred velocity only: the ALAN bandit (Python in the reference) is NOT included, which favours this arm"
+    sample = (f"{envs} of {cfg['envs']} envs x {cfg['agents']} agents per step, {threads} threads, {dt:.2f} s timed; {note}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_timed": envs, "agents_per_env": AGENTS,
-                   "note": "rvo2 (Python-RVO2) unavailable offline; oracle port of RVO2 timed on host cores"},
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * (cfg["envs"] / envs), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config_dict(cfg_name, cfg, args),
+        "notes": "rvo2 (Python-RVO2) unavailable offline; oracle port of RVO2 (oracle/rvo2_oracle.cpp) timed on host cores; "
+                 "ms_per_step is scaled to the full per-GPU batch",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -235,11 +264,56 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
-def run_ours(args):
+class GpuWorkload:
+    """One GPU's share of a BASELINE config: state on the device + the fused step."""
+
+    def __init__(self, cfg_name, cfg, dev, rank):
+        import torch
+        from collision_avoidance_b200 import _lib, alan
+        from collision_avoidance_b200.sim import BatchedRVOSimulator
+        self.torch, self._lib, self.cfg, self.name, self.dev = torch, _lib, cfg, cfg_name, dev
+        E, N = cfg["envs"], cfg["agents"]
+        self.E, self.N = E, N
+        self.alan = None
+        if cfg_name == "cfg3":
+            self.alan = alan.Collision_Avoidance_Sim(numAgents=N, scenario="circle", num_envs=E, seed=SEED + rank, device=dev)
+            self.sim = self.alan.sim
+            self.scn = self.alan.scn
+        else:
+            self.scn = _scenario(cfg, E, SEED + rank)
+            self.sim = BatchedRVOSimulator(E, N, device=dev, **self.scn.params)
+            self.sim.set_obstacles(self.scn.obstacles, per_env=self.scn.per_env_obstacles)
+        self.reset()
+
+    def reset(self):
+        torch, dev, E, N = self.torch, self.dev, self.E, self.N
+        if self.alan is not None:
+            self.alan.reset()
+            self.alan.sim.stats.zero_()
+            return
+        self.sim.pos.copy_(torch.from_numpy(self.scn.pos))
+        self.sim.vel.copy_(torch.from_numpy(self.scn.vel))
+        self.st = dict(goal=torch.from_numpy(self.scn.goal).to(dev), goal2=torch.from_numpy(self.scn.goal2).to(dev),
+                       agent_done=torch.zeros(E, N, dtype=torch.uint8, device=dev),
+                       arrival_time=torch.full((E, N), 0.0, device=dev),
+                       env_step=torch.zeros(E, dtype=torch.int32, device=dev),
+                       env_done_cnt=torch.zeros(E, dtype=torch.int32, device=dev))
+        self.sim.stats.zero_()
+
+    def step(self, steps=1):
+        if self.alan is not None:
+            self.alan.online_step(steps=steps)
+        else:
+            self.sim.env_step(policy=self._lib.POLICY_GOAL, done_mode=self._lib.DONE_GOAL_RADIUS_DEFERRED, steps=steps, **self.st)
+
+    def goal_tensor(self):
+        return self.alan.goal if self.alan is not None else self.st["goal"]
+
+
+def run_ours(args, cfg_name, cfg):
     import torch
     import torch.distributed as dist
-    from collision_avoidance_b200 import _lib, scenarios
-    from collision_avoidance_b200.sim import BatchedRVOSimulator
+    from collision_avoidance_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,27 +329,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    E, N = ENVS_PER_GPU, AGENTS
-    scn = scenarios.circle(E, N, seed=SEED + rank)
-    sim = BatchedRVOSimulator(E, N, device=dev, **scn.params)
-    sim.set_obstacles(scn.obstacles)
-
-    def reset_state():
-        sim.pos.copy_(torch.from_numpy(scn.pos))
-        sim.vel.copy_(torch.from_numpy(scn.vel))
-        st = dict(goal=torch.from_numpy(scn.goal).to(dev), goal2=torch.from_numpy(scn.goal2).to(dev),
-                  agent_done=torch.zeros(E, N, dtype=torch.uint8, device=dev),
-                  arrival_time=torch.full((E, N), 0.0, device=dev),
-                  env_step=torch.zeros(E, dtype=torch.int32, device=dev),
-                  env_done_cnt=torch.zeros(E, dtype=torch.int32, device=dev))
-        sim.stats.zero_()
-        return st
-
-    st = reset_state()
-
-    def step():
-        sim.env_step(policy=_lib.POLICY_GOAL, done_mode=_lib.DONE_GOAL_RADIUS, **st)
-
+    wl = GpuWorkload(cfg_name, cfg, dev, rank)
+    sim, E, N = wl.sim, wl.E, wl.N
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -284,9 +339,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-timed region -----------------------------------------------------------
+    # ---- device-timed region: fast-forward (untimed) -> W warm-up -> K timed steps -----------
+    if args.episode_step > 0:
+        wl.step(steps=args.episode_step)
     for _ in range(args.warmup):
-        step()
+        wl.step()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = sim.launch_count()
@@ -296,7 +353,7 @@ def run_ours(args):
         for i in range(args.steps):
             flush_buf.zero_()  # evict the state from L2 between timed launches
             starts[i].record()
-            step()
+            wl.step()
             ends[i].record()
         barrier()
         wall = time.perf_counter() - wall0
@@ -313,52 +370,107 @@ def run_ours(args):
     stats = sim.stats.clone()
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-    stats_d = {"finished": int(stats[_lib.STAT_FINISHED]), "collisions": int(stats[_lib.STAT_COLLISIONS]),
-               "lp3_calls": int(stats[_lib.STAT_LP3_CALLS]), "overflow": int(stats[_lib.STAT_OVERFLOW])}
+    stats_d = {"agent_steps": int(stats[_lib.STAT_AGENT_STEPS]), "finished": int(stats[_lib.STAT_FINISHED]),
+               "collisions": int(stats[_lib.STAT_COLLISIONS]), "lp3_calls": int(stats[_lib.STAT_LP3_CALLS]),
+               "overflow": int(stats[_lib.STAT_OVERFLOW])}
 
-    # ---- end-to-end region: host buffers through orca_step_host ---------------------------
-    pos_h = torch.from_numpy(scn.pos.copy()).pin_memory()
-    vel_h = torch.from_numpy(scn.vel.copy()).pin_memory()
-    goal_h = torch.from_numpy(scn.goal.copy()).pin_memory()
-    # same episode phase as the kernel-timed region: W steps from the reset state, then K timed
+    # ---- end-to-end region: host buffers through the C ABI, same episode phase ----------------
     e2e_steps = max(3, args.steps)
-    sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=max(1, args.warmup))
-    for _ in range(8):  # untimed: the library times both of its routes (direct / staged) on its first six steady calls and keeps the faster
-        sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        # per step: goals host->device (the setAgentPrefVelocity traffic), doStep, then
-        # positions + velocities device->host (the getAgentPosition/Velocity traffic)
-        sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
-    barrier()
-    e2e_dt = time.perf_counter() - t0
+    bytes_state = E * N * 8
+    if wl.alan is None:
+        pos_h = sim.pos.cpu().pin_memory()
+        vel_h = sim.vel.cpu().pin_memory()
+        goal_h = wl.goal_tensor().cpu().pin_memory()
+        sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=1)
+        for _ in range(8):  # untimed: the library times both of its routes (direct / staged) on its first six steady calls and keeps the faster
+            sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            # per step: goals host->device (the setAgentPrefVelocity traffic), doStep, then
+            # positions + velocities device->host (the getAgentPosition/Velocity traffic)
+            sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
+        barrier()
+        e2e_dt = time.perf_counter() - t0
+        h2d, d2h = bytes_state, 2 * bytes_state
+        e2e_api = ("BatchedRVOSimulator.step_host -> orca_step_host (pinned host buffers; the library keeps the faster of its "
+                   "two routes: kernel reads/writes the mapped host buffers directly, or chunked upload | step | download over streams)")
+    else:
+        # ALAN has no per-step host INPUT (actions are drawn on the device); what a host-side caller
+        # reads back every step is the reward, the chosen action and the done flags
+        rew_h = torch.empty(E, N, dtype=torch.float32).pin_memory()
+        act_h = torch.empty(E, N, dtype=torch.uint8).pin_memory()
+        done_h = torch.empty(E, N, dtype=torch.uint8).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            wl.alan.online_step()
+            rew_h.copy_(wl.alan.reward, non_blocking=True)
+            act_h.copy_(wl.alan.action_ids, non_blocking=True)
+            done_h.copy_(wl.alan.agents_done, non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        e2e_dt = time.perf_counter() - t0
+        h2d, d2h = 0, E * N * 6
+        e2e_api = ("alan.Collision_Avoidance_Sim.online_step + per-step device->host read of rewards, action ids and done flags "
+                   "(pinned buffers); the ALAN step has no per-step host input")
     te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * E * N * e2e_steps / float(te.item())
-    bytes_state = E * N * 8
+
+    # ---- cost profile over the episode (rank 0, untimed in the headline) -----------------------
+    by_phase, trace_mean = None, None
+    if rank == 0 and not args.no_phase_profile:
+        wl.reset()
+        by_phase, at, chunk_ms, chunk_steps = {}, 0, [], []
+        for target in PHASE_STEPS[cfg_name]:
+            if target > at:      # fast-forward, itself timed as one chunk (no L2 flush) for the episode mean
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                wl.step(steps=target - at)
+                e1.record()
+                torch.cuda.synchronize()
+                chunk_ms.append(e0.elapsed_time(e1))
+                chunk_steps.append(target - at)
+                at = target
+            ms = []
+            for _ in range(5):
+                flush_buf.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                wl.step()
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+                at += 1
+            by_phase[str(target)] = sum(ms) / len(ms)
+        trace_mean = sum(chunk_ms) / max(1, sum(chunk_steps))
 
     if rank == 0:
         peak, peak_src = _peaks()
         avg_kernel_s = (total_ms / args.steps) * 1e-3  # rank 0's own launches
-        achieved = BYTES_PER_AGENT_STEP * E * N / avg_kernel_s / 1e9
+        achieved = cfg["bytes"] * E * N / avg_kernel_s / 1e9
+        traffic, issue_profile = _static_profile(cfg_name)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents_per_env": N, "policy": "orca_step + done_test",
-                       "sharding": f"envs x{world}, no data-path collective", "l2": "flushed between timed launches "
-                       "(256 MiB memset; state is 41 MB/GPU, smaller than L2)", "timing": "CUDA events per launch, "
-                       "summed; max over ranks"},
+            "config": _config_dict(cfg_name, cfg, args),
+            "notes": {"sharding": f"envs x{world}, no data-path collective" if cfg["envs"] > 1 else f"{world} independent replicas",
+                      "l2": "flushed between timed launches (256 MiB memset; per-GPU state is smaller than L2)",
+                      "timing": "CUDA events per launch, summed; max over ranks",
+                      "window": f"state advanced untimed to episode step {args.episode_step}, then {args.warmup} warm-up and "
+                                f"{args.steps} timed steps"},
+            "ms_per_step_by_phase": by_phase, "episode_mean_ms_per_step": trace_mean,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _traffic(), "peak_source": peak_src,
-                         "bytes_per_agent_step": BYTES_PER_AGENT_STEP, "kernel": "step_small_kernel<10,GOAL>",
-                         "note": "kernel is instruction-issue / latency bound, not HBM bound; see DESIGN.md Roofline",
-                         "issue_profile": _issue_profile()},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_state,
-                    "d2h_bytes_per_step": 2 * bytes_state, "steps": e2e_steps,
-                    "api": "BatchedRVOSimulator.step_host -> orca_step_host (pinned host buffers; the library keeps the faster of its two routes: kernel reads/writes the mapped host buffers directly, or chunked upload | step | download over streams)"},
+                         "traffic": traffic, "traffic_static": True, "peak_source": peak_src,
+                         "bytes_per_agent_step": cfg["bytes"], "kernel": cfg["kernel"],
+                         "note": "kernel is instruction-issue / latency bound, not HBM bound; see DESIGN.md section 5; "
+                                 "traffic and issue_profile come from the committed ncu capture, not from this run",
+                         "issue_profile": issue_profile},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": e2e_api},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "host_affinity": {"rank0_cores": len(cores) if cores else None,
@@ -367,8 +479,8 @@ def run_ours(args):
             "episode_stats": stats_d,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.steps, args.warmup)
-            line["cpu_baseline_python_driver"] = cpu_python_driver_baseline()
+            line["cpu_baseline"] = cpu_baseline(cfg, args)
+            line["cpu_baseline_python_driver"] = cpu_python_driver_baseline(cfg)
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.barrier()
@@ -378,11 +490,18 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--episode-step", type=int, default=None,
+                    help="episode step the (untimed) fast-forward stops at before warm-up; default per config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-phase-profile", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.episode_step is None:
+        args.episode_step = cfg["episode_step"]
     # The contract is ONE JSON line on stdout.  Libraries may write there too (NCCL prints its
     # version banner to stdout when NCCL_DEBUG is set, as on the GPU boxes): keep a private handle on
     # the real stdout for the line and point fd 1 at stderr for everything else.
@@ -391,9 +510,9 @@ def main():
     _RESULT_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, args.config, cfg)
     else:
-        run_ours(args)
+        run_ours(args, args.config, cfg)
 
 
 if __name__ == "__main__":

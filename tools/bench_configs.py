@@ -47,7 +47,8 @@ def orca_policy(scn):
               agent_done=torch.zeros(E, N, dtype=torch.uint8, device="cuda"), arrival_time=torch.zeros(E, N, device="cuda"),
               env_step=torch.zeros(E, dtype=torch.int32, device="cuda"),
               env_done_cnt=torch.zeros(E, dtype=torch.int32, device="cuda"))
-    return sim, lambda: sim.env_step(policy=_lib.POLICY_GOAL, done_mode=_lib.DONE_GOAL_RADIUS, **st)
+    stats = not os.environ.get("BC_NO_STATS")
+    return sim, lambda: sim.env_step(policy=_lib.POLICY_GOAL, done_mode=_lib.DONE_GOAL_RADIUS_DEFERRED, collect_stats=stats, **st)
 
 
 def report(name, agents, ms, bytes_per, extra=None):
