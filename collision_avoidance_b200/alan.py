@@ -188,6 +188,7 @@ class Collision_Avoidance_Sim:
             self.step_count += chunk
             if bool(self.done_test().all()):
                 break
+        self.sim.check_overflow()   # loud, never silent: a dropped obstacle constraint voids the episode
         success = self.done_test()
         times = self.agents_time.double()
         self.TTime = times.mean(1) + 3 * times.std(1, unbiased=False)

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -188,10 +189,11 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   const size_t smem = orca::step_smem_bytes(K, tpb, true, args.world_slots);
   auto kern = orca::step_small_kernel<K, KFULL, POLICY>;
   // function attributes are per device: one flag per (instantiation, device)
-  static bool attr_set[orca::kMaxDevices] = {};
-  if (s->device >= orca::kMaxDevices || !attr_set[s->device]) {
+  // (distinct handles may be driven from distinct threads: atomic flags; setting the attribute twice is harmless)
+  static std::atomic<bool> attr_set[orca::kMaxDevices];
+  if (s->device >= orca::kMaxDevices || !attr_set[s->device].load(std::memory_order_acquire)) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::step_smem_bytes(K, 256, true, 256)));
-    if (s->device < orca::kMaxDevices) attr_set[s->device] = true;
+    if (s->device < orca::kMaxDevices) attr_set[s->device].store(true, std::memory_order_release);
   }
   kern<<<blocks, tpb, smem, st>>>(args);
   CUDA_TRY(cudaGetLastError());
@@ -821,13 +823,13 @@ int policy_mlp_common(OrcaSim* s, const float* obs_dev, int64_t rows, const Orca
   a.b3 = w->b3_dev;
   a.n_out = w->out_dim;
   a.out = out_dev;
-  static bool attr_set[orca::kMaxDevices] = {};  // function attributes are per device
+  static std::atomic<bool> attr_set[orca::kMaxDevices];  // function attributes are per device
   int sm_count = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, s->device));
-  if (s->device >= orca::kMaxDevices || !attr_set[s->device]) {
+  if (s->device >= orca::kMaxDevices || !attr_set[s->device].load(std::memory_order_acquire)) {
     CUDA_TRY(cudaFuncSetAttribute(orca::policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::mlp_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(orca::policy_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::mlp_tc_smem_bytes()));
-    if (s->device < orca::kMaxDevices) attr_set[s->device] = true;
+    if (s->device < orca::kMaxDevices) attr_set[s->device].store(true, std::memory_order_release);
   }
   if (tensor_cores) {
     const long long tiles = (rows + orca::kTcTile - 1) / orca::kTcTile;

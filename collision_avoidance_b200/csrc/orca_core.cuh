@@ -38,6 +38,12 @@
 #define ORCA_MAX_ACTIONS 16
 #endif
 #define ORCA_MAX_BSP_DEPTH 64
+// capacity of the uncapped ("slow") path taken by agents whose obstacle neighborhood exceeds the
+// fixed capacities above: obstacle neighbors AND obstacle lines of one agent.  An agent cannot see
+// more edges than the processed world has, so worlds of at most this many vertices can never overflow.
+#ifndef ORCA_SLOW_MAX_OBST
+#define ORCA_SLOW_MAX_OBST 64
+#endif
 
 #if defined(ORCA_EMUL_COUNT) && !defined(__CUDA_ARCH__)
 extern long long g_orca_counters[16];
@@ -696,6 +702,7 @@ struct CandidateBuffer {
 // Walks the BSP exactly like the recursive query (near side, node, far side if the splitting line
 // is within range) so that equal-distance edges keep RVO2's visiting order.  Result: edge ids
 // (first vertex of the edge) ascending by distance in od/oid, count in *cnt.
+template <int MAXN = ORCA_MAX_OBST_NEIGHBORS>
 ORCA_HD void obstacle_neighbors(const ObstacleWorld& W, float2 p, float range_sq, float* od, int* oid, int* cnt,
                                 bool* overflow) {
   int n = 0;
@@ -725,7 +732,7 @@ ORCA_HD void obstacle_neighbors(const ObstacleWorld& W, float2 p, float range_sq
         if (side < 0.f) {
           const float d = dist_sq_point_segment(p1, p2, p);
           if (d < range_sq) {
-            if (n < ORCA_MAX_OBST_NEIGHBORS) {
+            if (n < MAXN) {
               int i = n++;
               while (i != 0 && d < od[i - 1]) {
                 od[i] = od[i - 1];
@@ -736,7 +743,7 @@ ORCA_HD void obstacle_neighbors(const ObstacleWorld& W, float2 p, float range_sq
               oid[i] = v1;
             } else {
               *overflow = true;
-              // keep the nearest ORCA_MAX_OBST_NEIGHBORS: insert only if closer than the last
+              // keep the nearest MAXN: insert only if closer than the last
               if (d < od[n - 1]) {
                 int i = n - 1;
                 while (i != 0 && d < od[i - 1]) {
@@ -758,8 +765,8 @@ ORCA_HD void obstacle_neighbors(const ObstacleWorld& W, float2 p, float range_sq
 }
 
 // ---- obstacle half-planes (first half) ------------------------------------------------------
-// Appends at most ORCA_MAX_OBST_LINES lines to L starting at index 0; returns their number.
-template <class LS>
+// Appends at most MAXL lines to L starting at index 0; returns their number.
+template <int MAXL = ORCA_MAX_OBST_LINES, class LS>
 ORCA_HD int obstacle_lines(const ObstacleWorld& W, float2 p, float2 vel, float radius, float inv_tho,
                            const float* od, const int* oid, int cnt, const LS& L, bool* overflow) {
   (void)od;
@@ -918,7 +925,7 @@ ORCA_HD int obstacle_lines(const ObstacleWorld& W, float2 p, float2 vel, float r
       }
     }
     if (emit) {
-      if (nl < ORCA_MAX_OBST_LINES) {
+      if (nl < MAXL) {
         L.set(nl++, out_pt, out_dir);
       } else {
         *overflow = true;

@@ -3,12 +3,15 @@
 //
 // Replaces RVO2's per-step kd-tree (KdTree::buildAgentTree + queryAgentTreeRecursive, reached
 // through doStep: collision_avoidence_env.py:385,448 ; ALAN_true.py:601,632 ) by
-//   G1 grid_bounds    min/max of all positions                         (rd 8 B/agent)
-//   G2 grid_params    cell size = neighborDist, grid origin / dims     (1 thread)
-//   G3 grid_count     cell key per agent + slot inside the cell        (rd 8, wr 8, atomics)
-//   G4 grid_scan      exclusive scan of the cell populations           (3 small kernels)
-//   G5 grid_scatter   counting-sort scatter of pos / vel / id by cell  (rd 28, wr 20)
-//   G6 step_grid      fused step, candidates = the 3 x 3 cells around the agent
+// FIVE launches per step:
+//   G1 grid_bounds    min/max of all positions; the last block to finish derives the grid (cell
+//                     size = neighborDist, origin, dims) and re-arms the accumulators  (rd 8 B/agent)
+//   G2 grid_count     cell key per agent + slot inside the cell (atomics); also snapshots and
+//                     bumps the env step counters                              (rd 8, wr 8)
+//   G3 grid_scan      exclusive scan of the cell populations, ONE pass with decoupled look-back
+//                     (epoch-tagged tile states: nothing to reset); zeroes the counters it read
+//   G4 grid_scatter   counting-sort scatter of (pos, vel) as one float4 + id   (rd 28, wr 20)
+//   G5 step_grid      fused step, candidates = the 3 x 3 cells around the agent
 // A counting sort by cell key is all the "cell-key sort" this needs: keys are dense small
 // integers, and the order inside a cell is irrelevant because equal distances are ranked by
 // agent id (NearestK::offer_ranked), which also makes the result independent of the atomics'
@@ -24,6 +27,7 @@
 #include <cuda_runtime.h>
 #endif
 
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -48,28 +52,32 @@ ORCA_HD float grid_cell_size(float neighbor_dist) { return (neighbor_dist > 0.f 
 struct GridScratch {
   int T = 0;          // agents covered by the allocation
   int cap_cells = 0;  // capacity of the cell arrays
-  float2* sorted_pos = nullptr;
-  float2* sorted_vel = nullptr;
+  int E = 0;          // envs covered by the allocation
+  int sm_count = 0;   // multiprocessors of the device the scratch lives on
+  unsigned epoch = 0; // launch counter of the scan: tags the tile states, so they never need a reset
+  float4* sorted_pv = nullptr;  // (pos.x, pos.y, vel.x, vel.y) in cell order: the pre-step snapshot
   int* sorted_idx = nullptr;
   int* key = nullptr;
   int* slot = nullptr;
-  int* cell_count = nullptr;  // [cap_cells + 1]
+  int* cell_count = nullptr;  // [cap_cells + 1], all zero between steps (the scan re-zeroes what it reads)
   int* cell_start = nullptr;  // [cap_cells + 1]
-  int* block_sums = nullptr;  // [scan blocks + 1]
-  int* bounds = nullptr;      // 4 order-preserving ints: min x, min y, max x, max y
+  unsigned long long* tile_state = nullptr;  // [scan tiles] decoupled look-back states
+  int* counters = nullptr;    // [0..3] bounds (order-preserving ints: min x, min y, max x, max y),
+                              // [4] blocks of G1 that finished, [5] tile ticket of G3
+  int* env_step_snap = nullptr;  // [E] step counters as they were before this step
   GridParams* params = nullptr;
 };
 
 inline void grid_free(GridScratch& g) {
-  cudaFree(g.sorted_pos);
-  cudaFree(g.sorted_vel);
+  cudaFree(g.sorted_pv);
   cudaFree(g.sorted_idx);
   cudaFree(g.key);
   cudaFree(g.slot);
   cudaFree(g.cell_count);
   cudaFree(g.cell_start);
-  cudaFree(g.block_sums);
-  cudaFree(g.bounds);
+  cudaFree(g.tile_state);
+  cudaFree(g.counters);
+  cudaFree(g.env_step_snap);
   cudaFree(g.params);
   g = GridScratch();
 }
@@ -78,8 +86,7 @@ inline void grid_free(GridScratch& g) {
 // Candidates of an agent = agents in the 3 x 3 cells around it, read from the cell-sorted
 // snapshot.  Entries are identified by their sorted slot; `orig` maps a slot to the agent id.
 struct GridSource {
-  const float2* spos;
-  const float2* svel;
+  const float4* spv;  // (pos, vel) per sorted slot
   const int* orig;
   const int* cell_start;
   GridParams gp;
@@ -130,7 +137,7 @@ struct GridSource {
       // the position of the NEXT candidate is fetched while the current one is tested and parked:
       // the load (L1 / L2 latency) is the longest single wait of this loop
       float2 nxt = v2(0.f, 0.f);
-      if (q < last) nxt = ORCA_LDG(&spos[q]);
+      if (q < last) nxt = pos(q);
       // two candidates per pair of warp votes (loop condition, buffer check): the votes were a third
       // of this loop's instructions
       while (ORCA_ANY(mask, q < last)) {
@@ -140,7 +147,7 @@ struct GridSource {
             const float2 o = nxt;
             const int cur = q;
             ++q;
-            if (q < last) nxt = ORCA_LDG(&spos[q]);
+            if (q < last) nxt = pos(q);
             if (cur != self) {
               const float d = abs_sq(sub(p, o));
               if (d <= nk.thresh()) buf.push(d, cur);
@@ -152,8 +159,8 @@ struct GridSource {
     }
     buf.drain(mask, insert);
   }
-  ORCA_HD float2 pos(int q) const { return ORCA_LDG(&spos[q]); }
-  ORCA_HD float2 vel(int q) const { return ORCA_LDG(&svel[q]); }
+  ORCA_HD float2 pos(int q) const { return ORCA_LDG(reinterpret_cast<const float2*>(&spv[q])); }
+  ORCA_HD float2 vel(int q) const { return ORCA_LDG(reinterpret_cast<const float2*>(&spv[q]) + 1); }
   ORCA_HD int local_id(int q) const { return ORCA_LDG(&orig[q]) - env_n0; }
 };
 
@@ -166,39 +173,8 @@ __device__ __forceinline__ int float_to_ordered(float f) {
 }
 __device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-__global__ void grid_reset_kernel(int* bounds) {
-  bounds[0] = bounds[1] = 0x7fffffff;
-  bounds[2] = bounds[3] = (int)0x80000000;
-}
-
-__global__ void __launch_bounds__(256) grid_bounds_kernel(const float2* __restrict__ pos, int T, int* bounds) {
-  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
-    const float2 p = pos[i];
-    if (isfinite(p.x) && isfinite(p.y)) {
-      mnx = fminf(mnx, p.x);
-      mny = fminf(mny, p.y);
-      mxx = fmaxf(mxx, p.x);
-      mxy = fmaxf(mxy, p.y);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-    mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&bounds[0], float_to_ordered(mnx));
-    atomicMin(&bounds[1], float_to_ordered(mny));
-    atomicMax(&bounds[2], float_to_ordered(mxx));
-    atomicMax(&bounds[3], float_to_ordered(mxy));
-  }
-}
-
-// One thread: grid origin / dims; the cell is enlarged if the box would need more cells than allocated.
-__global__ void grid_params_kernel(const int* bounds, float neighbor_dist, int E, int cap_cells, GridParams* out) {
+// Grid geometry from the bounding box; the cell is enlarged if the box would need more cells than allocated.
+__device__ __forceinline__ void grid_derive_params(const int* bounds, float neighbor_dist, int E, int cap_cells, GridParams* out) {
   float mnx = ordered_to_float(bounds[0]), mny = ordered_to_float(bounds[1]);
   float mxx = ordered_to_float(bounds[2]), mxy = ordered_to_float(bounds[3]);
   if (!(mnx <= mxx) || !(mny <= mxy)) {
@@ -224,10 +200,94 @@ __global__ void grid_params_kernel(const int* bounds, float neighbor_dist, int E
   out->ncells = E * W * H;
 }
 
+__global__ void grid_arm_kernel(int* counters) {  // first use only: the kernels re-arm the counters themselves
+  counters[0] = counters[1] = 0x7fffffff;
+  counters[2] = counters[3] = (int)0x80000000;
+  counters[4] = counters[5] = 0;
+}
+
+// G1: bounding box of all positions -> grid geometry.  One atomic quadruple per BLOCK (it was one per
+// warp: 19,000 same-address atomics took longer than reading the positions); the block that finishes
+// last derives the geometry and re-arms the accumulators for the next step, so neither a reset nor a
+// parameter kernel is launched.
+constexpr int kBoundsThreads = 512;
+__global__ void __launch_bounds__(kBoundsThreads) grid_bounds_kernel(const float2* __restrict__ pos, int T, int* counters,
+                                                                      float neighbor_dist, int E, int cap_cells,
+                                                                      GridParams* params) {
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
+    const float2 p = pos[i];
+    if (isfinite(p.x) && isfinite(p.y)) {
+      mnx = fminf(mnx, p.x);
+      mny = fminf(mny, p.y);
+      mxx = fmaxf(mxx, p.x);
+      mxy = fmaxf(mxy, p.y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  __shared__ float s_red[4][kBoundsThreads / 32];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_red[0][warp] = mnx;
+    s_red[1][warp] = mny;
+    s_red[2][warp] = mxx;
+    s_red[3][warp] = mxy;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const bool in = lane < kBoundsThreads / 32;
+    mnx = in ? s_red[0][lane] : INFINITY;
+    mny = in ? s_red[1][lane] : INFINITY;
+    mxx = in ? s_red[2][lane] : -INFINITY;
+    mxy = in ? s_red[3][lane] : -INFINITY;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+      mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+      mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+      mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if (lane == 0) {
+      atomicMin(&counters[0], float_to_ordered(mnx));
+      atomicMin(&counters[1], float_to_ordered(mny));
+      atomicMax(&counters[2], float_to_ordered(mxx));
+      atomicMax(&counters[3], float_to_ordered(mxy));
+      __threadfence();
+      s_last = atomicAdd(&counters[4], 1) == (int)gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    int b[4];
+    for (int i = 0; i < 4; ++i) b[i] = atomicAdd(&counters[i], 0);  // the other blocks' atomics, read at L2
+    grid_derive_params(b, neighbor_dist, E, cap_cells, params);
+    counters[0] = counters[1] = 0x7fffffff;
+    counters[2] = counters[3] = (int)0x80000000;
+    counters[4] = 0;
+  }
+}
+
+// G2: cell key + slot per agent.  Its first E threads also copy the env step counters aside and bump
+// them: an env spans many blocks of the step kernel, so those read the copy while the caller's
+// counters already hold the value the call leaves behind.
 __global__ void __launch_bounds__(256) grid_count_kernel(const float2* __restrict__ pos, int T, int N,
                                                          const GridParams* __restrict__ gpp, int* cell_count,
-                                                         int* __restrict__ key, int* __restrict__ slot) {
+                                                         int* __restrict__ key, int* __restrict__ slot, int* env_step,
+                                                         int* __restrict__ env_step_snap, int E, int bump) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env_step != nullptr && i < E) {
+    const int s0 = env_step[i];
+    env_step_snap[i] = s0;
+    if (bump) env_step[i] = s0 + 1;
+  }
   if (i >= T) return;
   const GridParams gp = *gpp;
   const float2 p = pos[i];
@@ -238,7 +298,12 @@ __global__ void __launch_bounds__(256) grid_count_kernel(const float2* __restric
   slot[i] = atomicAdd(&cell_count[k], 1);
 }
 
-// ---- exclusive scan of cell_count[0 .. ncells] into cell_start (ncells + 1 entries) -----------------
+// ---- G3: exclusive scan of cell_count[0 .. ncells) into cell_start (ncells + 1 entries) --------------
+// Single pass, decoupled look-back (Merrill & Garland): a block takes the next tile from a ticket
+// counter, publishes the tile's sum, walks back over its predecessors' states until it meets an
+// inclusive prefix, publishes its own.  A state word = epoch << 34 | flag << 32 | value; states of an
+// earlier launch carry an older epoch and read as "not there yet", so nothing is ever cleared.
+// The counters a tile has read are zeroed on the way: cell_count is all zero again for the next step.
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;  // per thread
 constexpr int kScanTile = kScanThreads * kScanItems;
@@ -270,51 +335,54 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
   return warp_off + inc - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads) grid_scan_partial_kernel(const int* __restrict__ cnt,
-                                                                         const GridParams* __restrict__ gpp,
-                                                                         int* __restrict__ block_sums) {
-  const int n = gpp->ncells;
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-  if (blockIdx.x * kScanTile >= n) return;
-  int s = 0;
-#pragma unroll
-  for (int t = 0; t < kScanItems; ++t) s += (base + t < n) ? cnt[base + t] : 0;
-  int total;
-  block_exclusive_scan(s, &total);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(kScanThreads) grid_scan_sums_kernel(int* block_sums,
-                                                                      const GridParams* __restrict__ gpp) {
-  // single block: exclusive scan of the per-tile totals, in chunks of kScanThreads
-  const int nb = (gpp->ncells + kScanTile - 1) / kScanTile;
-  int carry = 0;
-  for (int c0 = 0; c0 < nb; c0 += kScanThreads) {
-    const int i = c0 + threadIdx.x;
-    const int v = i < nb ? block_sums[i] : 0;
-    int total;
-    const int ex = block_exclusive_scan(v, &total);
-    if (i < nb) block_sums[i] = carry + ex;
-    carry += total;
+__global__ void __launch_bounds__(kScanThreads) grid_scan_kernel(int* __restrict__ cnt, const GridParams* __restrict__ gpp,
+                                                                 unsigned long long* tile_state, int* ticket,
+                                                                 unsigned epoch, int* __restrict__ start) {
+  __shared__ int s_tile, s_prefix;
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(ticket, 1);
+    if (t == (int)gridDim.x - 1) *ticket = 0;  // every block has drawn: re-arm for the next launch
+    s_tile = t;
   }
-}
-
-__global__ void __launch_bounds__(kScanThreads) grid_scan_final_kernel(const int* __restrict__ cnt,
-                                                                       const GridParams* __restrict__ gpp,
-                                                                       const int* __restrict__ block_sums,
-                                                                       int* __restrict__ start) {
+  __syncthreads();
+  const int tile = s_tile;
   const int n = gpp->ncells;
-  if (blockIdx.x * kScanTile >= n) return;
-  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  if (tile * kScanTile >= n) return;  // tiles are handed out in order: everything in front of a live tile is live
+  const int base = tile * kScanTile + threadIdx.x * kScanItems;
   int v[kScanItems];
   int s = 0;
 #pragma unroll
   for (int t = 0; t < kScanItems; ++t) {
-    v[t] = (base + t < n) ? cnt[base + t] : 0;
+    v[t] = 0;
+    if (base + t < n) {
+      v[t] = cnt[base + t];
+      cnt[base + t] = 0;
+    }
     s += v[t];
   }
   int total;
-  int off = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+  const int local = block_exclusive_scan(s, &total);
+  const unsigned long long tag = (unsigned long long)epoch << 34;
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* st = tile_state;
+    int prefix = 0;
+    if (tile > 0) {
+      st[tile] = tag | (1ull << 32) | (unsigned)total;  // aggregate available
+      for (int p = tile - 1; p >= 0; --p) {
+        unsigned long long w;
+        do {
+          w = st[p];
+        } while ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0ull);
+        prefix += (int)(unsigned)(w & 0xffffffffull);
+        if (((w >> 32) & 3ull) == 2ull) break;  // an inclusive prefix: nothing further back is needed
+      }
+    }
+    __threadfence();
+    st[tile] = tag | (2ull << 32) | (unsigned)(prefix + total);  // inclusive prefix available
+    s_prefix = prefix;
+  }
+  __syncthreads();
+  int off = local + s_prefix;
 #pragma unroll
   for (int t = 0; t < kScanItems; ++t) {
     if (base + t < n) start[base + t] = off;
@@ -323,15 +391,16 @@ __global__ void __launch_bounds__(kScanThreads) grid_scan_final_kernel(const int
   }
 }
 
+// G4: one 16-byte store of (pos, vel) + one 4-byte store of the id per agent, to its sorted slot
 __global__ void __launch_bounds__(256) grid_scatter_kernel(const float2* __restrict__ pos, const float2* __restrict__ vel,
                                                            int T, const int* __restrict__ key, const int* __restrict__ slot,
-                                                           const int* __restrict__ cell_start, float2* __restrict__ spos,
-                                                           float2* __restrict__ svel, int* __restrict__ sidx) {
+                                                           const int* __restrict__ cell_start, float4* __restrict__ spv,
+                                                           int* __restrict__ sidx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T) return;
   const int j = cell_start[key[i]] + slot[i];
-  spos[j] = pos[i];
-  svel[j] = vel[i];
+  const float2 p = pos[i], v = vel[i];
+  spv[j] = make_float4(p.x, p.y, v.x, v.y);
   sidx[j] = i;
 }
 
@@ -341,10 +410,11 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float2* __restr
 // G6: the fused step over the cell-sorted order.  Thread j handles the agent in sorted slot j, so a
 // warp's agents share cells (coherent candidate loops, cache-friendly reads).
 template <int K, bool KFULL, int POLICY>
-__global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_kernel(const StepArgs a, const float2* __restrict__ spos,
-                                                           const float2* __restrict__ svel, const int* __restrict__ sidx,
+__global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_kernel(const StepArgs a, const float4* __restrict__ spv,
+                                                           const int* __restrict__ sidx,
                                                            const int* __restrict__ cell_start,
-                                                           const GridParams* __restrict__ gpp) {
+                                                           const GridParams* __restrict__ gpp,
+                                                           const int* __restrict__ env_step_snap) {
   extern __shared__ float4 smem4[];
   const int tpb = blockDim.x;
   float4* s_lines = smem4;
@@ -365,14 +435,14 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_
   c.n = c.n_obst = c.fail = 0;
   int g = 0, env = 0, la = 0, estep = 0;
   bool alive = valid;
+  c.overflow = false;
+  GridSource src;
   if (valid) {
     g = sidx[j];
     env = g / a.N;
     la = g - env * a.N;
-    estep = (a.env_step != nullptr) ? a.env_step[env] : 0;
-    GridSource src;
-    src.spos = spos;
-    src.svel = svel;
+    estep = (a.env_step != nullptr) ? env_step_snap[env] : 0;
+    src.spv = spv;
     src.orig = sidx;
     src.cell_start = cell_start;
     src.gp = *gpp;
@@ -382,23 +452,24 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_
     Lines L;
     L.base = s_lines + threadIdx.x;
     L.stride = tpb;
-    c.p = spos[j];
-    c.v = svel[j];
+    const float4 pv = spv[j];
+    c.p = v2(pv.x, pv.y);
+    c.v = v2(pv.z, pv.w);
     if (!a.neighbors_only) c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];
     alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
-  block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax);
+  block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && !c.overflow && c.fail < c.n, c, a.vmax);
+  const unsigned slow_mask = __ballot_sync(0xffffffffu, alive && c.overflow);
   if (!alive) return;
   c.nv = s_nv[threadIdx.x];
+  if (c.overflow) {  // rare: more obstacle edges / lines than the fast path holds (see agent_slow_path)
+    Lines L;
+    L.base = s_lines + threadIdx.x;
+    L.stride = tpb;
+    agent_slow_path<K, KFULL>(a, src, global_world(a, env), L, slow_mask, c);
+  }
   agent_back<POLICY>(a, env, la, g, estep, c);
-}
-
-// env_step counters are bumped by a separate tiny kernel in the grid path: an env spans many
-// blocks, so no thread of the step kernel may write the counter its siblings still read.
-__global__ void grid_bump_env_step_kernel(int* env_step, int E) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < E) env_step[e] += 1;
 }
 
 #define ORCA_GRID_TRY(expr)                                                         \
@@ -412,41 +483,42 @@ __global__ void grid_bump_env_step_kernel(int* env_step, int E) {
 
 inline int grid_ensure(GridScratch& G, const StepArgs& a, cudaStream_t st, std::string* err) {
   const int T = a.E * a.N;
-  if (G.T == T && G.sorted_pos != nullptr) return 0;
+  if (G.T == T && G.E == a.E && G.sorted_pv != nullptr) return 0;
   grid_free(G);
+  int dev = 0;
+  ORCA_GRID_TRY(cudaGetDevice(&dev));
+  ORCA_GRID_TRY(cudaDeviceGetAttribute(&G.sm_count, cudaDevAttrMultiProcessorCount, dev));
   // size the cell arrays from the current extent of the world (one host sync, first call only)
-  ORCA_GRID_TRY(cudaMalloc(&G.bounds, 4 * sizeof(int)));
+  ORCA_GRID_TRY(cudaMalloc(&G.counters, 8 * sizeof(int)));
   ORCA_GRID_TRY(cudaMalloc(&G.params, sizeof(GridParams)));
-  grid_reset_kernel<<<1, 1, 0, st>>>(G.bounds);
-  grid_bounds_kernel<<<148 * 4, 256, 0, st>>>(a.pos, T, G.bounds);
-  int hb[4];
-  ORCA_GRID_TRY(cudaMemcpyAsync(hb, G.bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  grid_arm_kernel<<<1, 1, 0, st>>>(G.counters);
+  grid_bounds_kernel<<<G.sm_count * 2, kBoundsThreads, 0, st>>>(a.pos, T, G.counters, sqrtf(a.nd_sq), a.E, 1 << 30, G.params);
+  GridParams hp;
+  ORCA_GRID_TRY(cudaMemcpyAsync(&hp, G.params, sizeof(hp), cudaMemcpyDeviceToHost, st));
   ORCA_GRID_TRY(cudaStreamSynchronize(st));
-  auto dec = [](int i) {
-    const int b = i >= 0 ? i : i ^ 0x7fffffff;
-    float f;
-    memcpy(&f, &b, 4);
-    return f;
-  };
-  const float cell = grid_cell_size(sqrtf(a.nd_sq));
-  double w = (double)dec(hb[2]) - (double)dec(hb[0]), h = (double)dec(hb[3]) - (double)dec(hb[1]);
-  if (!(w >= 0) || !(h >= 0)) w = h = 0;
   // room for the world to spread to ~2x its current side before the cell size has to grow
-  double cells = (2.0 * w / cell + 2.0) * (2.0 * h / cell + 2.0) * (double)a.E;
+  double cells = (2.0 * hp.W + 2.0) * (2.0 * hp.H + 2.0) * (double)a.E;
   if (cells < 1024) cells = 1024;
   if (cells > 1.6e7) cells = 1.6e7;
   G.cap_cells = (int)cells;
   G.T = T;
-  ORCA_GRID_TRY(cudaMalloc(&G.sorted_pos, (size_t)T * sizeof(float2)));
-  ORCA_GRID_TRY(cudaMalloc(&G.sorted_vel, (size_t)T * sizeof(float2)));
+  G.E = a.E;
+  G.epoch = 0;
+  const size_t tiles = ((size_t)G.cap_cells + kScanTile - 1) / kScanTile;
+  ORCA_GRID_TRY(cudaMalloc(&G.sorted_pv, (size_t)T * sizeof(float4)));
   ORCA_GRID_TRY(cudaMalloc(&G.sorted_idx, (size_t)T * sizeof(int)));
   ORCA_GRID_TRY(cudaMalloc(&G.key, (size_t)T * sizeof(int)));
   ORCA_GRID_TRY(cudaMalloc(&G.slot, (size_t)T * sizeof(int)));
   ORCA_GRID_TRY(cudaMalloc(&G.cell_count, ((size_t)G.cap_cells + 1) * sizeof(int)));
   ORCA_GRID_TRY(cudaMalloc(&G.cell_start, ((size_t)G.cap_cells + 1) * sizeof(int)));
-  ORCA_GRID_TRY(cudaMalloc(&G.block_sums, ((size_t)G.cap_cells / kScanTile + 2) * sizeof(int)));
+  ORCA_GRID_TRY(cudaMalloc(&G.tile_state, tiles * sizeof(unsigned long long)));
+  ORCA_GRID_TRY(cudaMalloc(&G.env_step_snap, (size_t)a.E * sizeof(int)));
+  ORCA_GRID_TRY(cudaMemsetAsync(G.cell_count, 0, ((size_t)G.cap_cells + 1) * sizeof(int), st));
+  ORCA_GRID_TRY(cudaMemsetAsync(G.tile_state, 0, tiles * sizeof(unsigned long long), st));
   return 0;
 }
+
+constexpr int kGridLaunchesPerStep = 5;  // G1 bounds, G2 count, G3 scan, G4 scatter, G5 step
 
 template <int K, bool KFULL, int POLICY>
 int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* launches, std::string* err) {
@@ -455,39 +527,32 @@ int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* 
   if (rc != 0) return rc;
   const int tpb = 256;
   const int nb_agents = (T + tpb - 1) / tpb;
-  grid_reset_kernel<<<1, 1, 0, st>>>(G.bounds);
-  grid_bounds_kernel<<<148 * 4, 256, 0, st>>>(a.pos, T, G.bounds);
-  grid_params_kernel<<<1, 1, 0, st>>>(G.bounds, sqrtf(a.nd_sq), a.E, G.cap_cells, G.params);
-  ORCA_GRID_TRY(cudaMemsetAsync(G.cell_count, 0, ((size_t)G.cap_cells + 1) * sizeof(int), st));
-  grid_count_kernel<<<nb_agents, tpb, 0, st>>>(a.pos, T, a.N, G.params, G.cell_count, G.key, G.slot);
+  grid_bounds_kernel<<<G.sm_count * 2, kBoundsThreads, 0, st>>>(a.pos, T, G.counters, sqrtf(a.nd_sq), a.E, G.cap_cells, G.params);
+  grid_count_kernel<<<nb_agents, tpb, 0, st>>>(a.pos, T, a.N, G.params, G.cell_count, G.key, G.slot, a.env_step,
+                                               G.env_step_snap, a.E, a.neighbors_only ? 0 : 1);
   const int scan_blocks = (G.cap_cells + kScanTile - 1) / kScanTile;
-  grid_scan_partial_kernel<<<scan_blocks, kScanThreads, 0, st>>>(G.cell_count, G.params, G.block_sums);
-  grid_scan_sums_kernel<<<1, kScanThreads, 0, st>>>(G.block_sums, G.params);
-  grid_scan_final_kernel<<<scan_blocks, kScanThreads, 0, st>>>(G.cell_count, G.params, G.block_sums, G.cell_start);
-  grid_scatter_kernel<<<nb_agents, tpb, 0, st>>>(a.pos, a.vel, T, G.key, G.slot, G.cell_start, G.sorted_pos,
-                                                 G.sorted_vel, G.sorted_idx);
+  G.epoch = (G.epoch + 1u) & 0x3fffffffu;
+  if (G.epoch == 0u) G.epoch = 1u;  // 0 is the state of freshly cleared words
+  grid_scan_kernel<<<scan_blocks, kScanThreads, 0, st>>>(G.cell_count, G.params, G.tile_state, G.counters + 5, G.epoch,
+                                                        G.cell_start);
+  grid_scatter_kernel<<<nb_agents, tpb, 0, st>>>(a.pos, a.vel, T, G.key, G.slot, G.cell_start, G.sorted_pv, G.sorted_idx);
   StepArgs args = a;
-  int* env_step = args.env_step;
-  // the step kernel only READS the counters in this path (see grid_bump_env_step_kernel)
+  // the step kernel only READS the step counters in this path, from the copy G2 made
   const int stpb = ORCA_GRID_TPB;
   const size_t smem = step_smem_bytes(K, stpb, false);
   auto kern = step_grid_kernel<K, KFULL, POLICY>;
-  static bool attr_set[kMaxDevices] = {};  // function attributes are per device
   int dev = 0;
   ORCA_GRID_TRY(cudaGetDevice(&dev));
-  if (dev >= kMaxDevices || !attr_set[dev]) {
+  // function attributes are per device; setting one is idempotent, so a racing second thread is harmless
+  static std::atomic<bool> attr_set[kMaxDevices];
+  if (dev >= kMaxDevices || !attr_set[dev].load(std::memory_order_acquire)) {
     ORCA_GRID_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (dev < kMaxDevices) attr_set[dev] = true;
+    if (dev < kMaxDevices) attr_set[dev].store(true, std::memory_order_release);
   }
   args.grid_path = 1;
-  kern<<<(T + stpb - 1) / stpb, stpb, smem, st>>>(args, G.sorted_pos, G.sorted_vel, G.sorted_idx, G.cell_start, G.params);
-  int n_launch = 9;
-  if (env_step != nullptr && !a.neighbors_only) {
-    grid_bump_env_step_kernel<<<(a.E + 255) / 256, 256, 0, st>>>(env_step, a.E);
-    ++n_launch;
-  }
+  kern<<<(T + stpb - 1) / stpb, stpb, smem, st>>>(args, G.sorted_pv, G.sorted_idx, G.cell_start, G.params, G.env_step_snap);
   ORCA_GRID_TRY(cudaGetLastError());
-  *launches += n_launch;
+  *launches += kGridLaunchesPerStep;
   return 0;
 }
 

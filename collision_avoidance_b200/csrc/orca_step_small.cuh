@@ -500,6 +500,53 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
   return true;
 }
 
+// The uncapped path.  RVO2 keeps EVERY obstacle edge in range and every ORCA line built from them
+// (insertObstacleNeighbor has no cap); the front half above holds 16 edges and 6
+// obstacle lines per agent in registers / shared memory, which covers every agent of every
+// scenario of the reference.  An agent that exceeds either capacity is redone here from scratch
+// with room for ORCA_SLOW_MAX_OBST edges and lines in LOCAL memory: same neighbor search, same
+// half-planes, same LP2 / LP3 (projections recomputed on access), so it gets exactly the result an
+// unbounded implementation gives.  Not inlined: the hot code does not grow.  `mask` = the lanes of
+// the warp that take this path together.  `scratch` = the agent's own (now dead) line column, used
+// by the neighbor search as candidate buffer.  Leaves c.overflow set only if even this capacity
+// was exceeded (the statistic the shells turn into an error).
+template <int K, bool KFULL, class Src>
+ORCA_HD_NOINLINE void agent_slow_path(const StepArgs& a, const Src& src, const ObstacleWorld& W, const Lines scratch,
+                                      const unsigned mask, AgentCarry& c) {
+  const float2 p = c.p, v = c.v;
+  bool overflow = false;
+  float od[ORCA_SLOW_MAX_OBST];
+  int oid[ORCA_SLOW_MAX_OBST];
+  int ocnt = 0;
+  obstacle_neighbors<ORCA_SLOW_MAX_OBST>(W, p, a.obst_range_sq, od, oid, &ocnt, &overflow);
+  float4 buf[ORCA_SLOW_MAX_OBST + K];
+  Lines L;
+  L.base = buf;
+  L.stride = 1;
+  const int n_obst = obstacle_lines<ORCA_SLOW_MAX_OBST>(W, p, v, a.radius, a.inv_tho, od, oid, ocnt, L, &overflow);
+  typename Src::template List<K, KFULL> nk;
+  nk.init(a.k, a.nd_sq);
+  src.gather(nk, p, scratch, K + ORCA_MAX_OBST_LINES, mask);
+  if (nk.packed_cnt >= 0) nk.unpack_ids();
+  int n = n_obst;
+  unsigned collisions = 0;
+  const float cr = a.radius + a.radius;
+  for (int s = 0; s < K; ++s) {
+    const int j = nk.id[s];
+    if (j >= 0) {
+      bool hit;
+      buf[n++] = agent_line(p, v, src.pos(j), src.vel(j), cr, a.inv_th, a.inv_dt, &hit);
+      collisions += hit ? 1u : 0u;
+    }
+  }
+  c.n = n;
+  c.n_obst = n_obst;
+  c.collisions = collisions;
+  c.overflow = overflow;
+  c.fail = lp2(mask, true, L, n, a.vmax, c.pref, false, c.nv);
+  lp3(mask, c.fail < n, L, n, n_obst, c.fail, a.vmax, c.nv);
+}
+
 // Back half: Agent::update + reward + bandit update + done test, with c.nv final.
 template <int POLICY>
 ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const int g, const int estep,
@@ -584,7 +631,10 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
   c.v = v;
   c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];
   if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c)) return;
-  lp3(warp_mask, c.fail < c.n, L, c.n, c.n_obst, c.fail, a.vmax, c.nv);
+  if (c.overflow)
+    agent_slow_path<K, KFULL>(a, src, global_world(a, env), L, warp_mask, c);
+  else
+    lp3(warp_mask, c.fail < c.n, L, c.n, c.n_obst, c.fail, a.vmax, c.nv);
   agent_back<POLICY>(a, env, la, g, estep, c);
 }
 
@@ -844,8 +894,11 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   TileSource src;
   const bool tile_grid = a.tile_grid_inv_cell > 0.f;  // uniform over the grid
   if (tile_grid) build_tile_grid(a, s_nv, valid, le, la, c.p, src);
+  ObstacleWorld W;
+  W.n_nodes = 0;
+  c.overflow = false;
   if (valid) {
-    ObstacleWorld W = global_world(a, env);
+    W = global_world(a, env);
     if (slots > 0) {
       const int off = le * a.vert_stride;  // 0 for a shared world
       W.vert_pd = s_world + off;
@@ -863,9 +916,16 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
     alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, W, L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
-  block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && c.fail < c.n, c, a.vmax, tile_grid);
+  block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && !c.overflow && c.fail < c.n, c, a.vmax, tile_grid);
+  const unsigned slow_mask = __ballot_sync(0xffffffffu, alive && c.overflow);
   if (!alive) return;
   c.nv = s_nv[tid];
+  if (c.overflow) {  // rare: more obstacle edges / lines than the fast path holds
+    Lines L;
+    L.base = s_lines + tid;
+    L.stride = tpb;
+    agent_slow_path<K, KFULL>(a, src, W, L, slow_mask, c);
+  }
   agent_back<POLICY>(a, env, la, g, estep, c);
 }
 

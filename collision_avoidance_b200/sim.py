@@ -287,7 +287,19 @@ class BatchedRVOSimulator:
     def launch_count(self) -> int:
         return int(self._L.orca_launch_count(self._h))
 
-    def read_stats(self) -> dict:
+    def check_overflow(self):
+        """Raises if any agent exceeded even the uncapped path's capacity (ORCA_SLOW_MAX_OBST = 64
+        obstacle edges in range / obstacle lines): from then on an obstacle constraint is missing from
+        that agent's linear program, which RVO2 never allows.  Cannot happen for obstacle worlds of at
+        most 64 processed vertices (every world of the reference has fewer)."""
+        n = int(self.stats[_lib.STAT_OVERFLOW].item())
+        if n:
+            raise RuntimeError(f"{n} agent-steps exceeded the obstacle capacity of the step kernel (64 edges / lines per "
+                               "agent): results are no longer RVO2's; simplify the obstacle world")
+
+    def read_stats(self, allow_overflow: bool = False) -> dict:
+        if not allow_overflow:
+            self.check_overflow()
         s = self.stats.cpu()
         f = s.view(torch.float64)
         return {

@@ -106,14 +106,20 @@ void run_grid_k(const orca::StepArgs& a0, int policy) {
   // reversed agent order inside each cell on purpose: the result must not depend on it
   for (int i = T - 1; i >= 0; --i) sidx[(size_t)fill[(size_t)key[(size_t)i]]++] = i;
   std::vector<float2> spos((size_t)T), svel((size_t)T);
-  for (int j = 0; j < T; ++j) { spos[(size_t)j] = a.pos[sidx[(size_t)j]]; svel[(size_t)j] = a.vel[sidx[(size_t)j]]; }
+  std::vector<float4> spv((size_t)T);
+  for (int j = 0; j < T; ++j) {
+    spos[(size_t)j] = a.pos[sidx[(size_t)j]];
+    svel[(size_t)j] = a.vel[sidx[(size_t)j]];
+    spv[(size_t)j].x = spos[(size_t)j].x; spv[(size_t)j].y = spos[(size_t)j].y;
+    spv[(size_t)j].z = svel[(size_t)j].x; spv[(size_t)j].w = svel[(size_t)j].y;
+  }
   std::vector<int> estep0((size_t)E, 0);
   if (a.env_step) for (int e = 0; e < E; ++e) estep0[(size_t)e] = a.env_step[e];
   std::vector<float4> lines((size_t)(K + ORCA_MAX_OBST_LINES));
   for (int j = 0; j < T; ++j) {
     const int g = sidx[(size_t)j], env = g / N, la = g - env * N;
     orca::GridSource src;
-    src.spos = spos.data(); src.svel = svel.data(); src.orig = sidx.data(); src.cell_start = start.data();
+    src.spv = spv.data(); src.orig = sidx.data(); src.cell_start = start.data();
     src.gp = gp; src.env = env; src.env_n0 = env * N; src.self = j;
     orca::Lines L; L.base = lines.data(); L.stride = 1;
     const int es = estep0[(size_t)env];

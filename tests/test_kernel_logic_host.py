@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import _emul
-from _common import goal_pref, neighbor_sets_equal_up_to_ties, oracle_sims, snake
+from _common import goal_pref, neighbor_sets_equal_up_to_ties, oracle_sims, pillar_hall, snake
 from collision_avoidance_b200 import scenarios
 
 
@@ -202,3 +202,31 @@ def test_observation_logic_matches_shell_oracle():
     assert hits > 0.1 * rays          # the scans are not trivially empty
     assert worst <= 2e-4
     assert flips <= 0.002 * rays
+
+
+def test_uncapped_obstacle_path_matches_the_oracle():
+    """RVO2 keeps every obstacle edge in range and every line built from them; agents that exceed
+    the fast path's 16 / 6 are redone by agent_slow_path with room for 64: bit-identical to the
+    oracle, and the overflow statistic stays 0."""
+    scn = pillar_hall()
+    P = snake(scn.params)
+    world = _emul.World(scn.obstacles)
+    assert world.nv <= 64
+    sims = oracle_sims(scn)
+    stats = np.zeros(8, np.uint64)
+    most_nbrs = most_lines = 0
+    for t in range(260):
+        pos = np.stack([s.positions() for s in sims])
+        vel = np.stack([s.velocities() for s in sims])
+        pref = goal_pref(pos, scn.goal).astype(np.float32)
+        sims[0].set_pref_velocities(pref[0])
+        sims[0].doStep()
+        pe, ve = pos.copy(), vel.copy()
+        _emul.emul_step(P, pe, ve, policy=0, pref=np.ascontiguousarray(pref), world=world, stats=stats)
+        assert np.array_equal(ve[0], sims[0].velocities()), t
+        assert np.array_equal(pe[0], sims[0].positions()), t
+        for i in range(scn.agents_per_env):
+            most_nbrs = max(most_nbrs, len(sims[0].obstacle_neighbors(i)))
+            most_lines = max(most_lines, sims[0].orca_lines(i)[1])
+    assert most_nbrs > 16 and most_lines > 6, (most_nbrs, most_lines)
+    assert stats[4] == 0          # ORCA_STAT_OVERFLOW: nothing exceeded the slow path
