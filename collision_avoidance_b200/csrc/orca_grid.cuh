@@ -436,12 +436,12 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_
   int g = 0, env = 0, la = 0, estep = 0;
   bool alive = valid;
   c.overflow = false;
-  GridSource src;
   if (valid) {
     g = sidx[j];
     env = g / a.N;
     la = g - env * a.N;
     estep = (a.env_step != nullptr) ? env_step_snap[env] : 0;
+    GridSource src;
     src.spv = spv;
     src.orig = sidx;
     src.cell_start = cell_start;
@@ -464,10 +464,20 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_
   if (!alive) return;
   c.nv = s_nv[threadIdx.x];
   if (c.overflow) {  // rare: more obstacle edges / lines than the fast path holds (see agent_slow_path)
+    // the neighbor source is rebuilt here from the kernel arguments: nothing of the hot path has to
+    // live in local memory for the sake of this call
     Lines L;
     L.base = s_lines + threadIdx.x;
     L.stride = tpb;
-    agent_slow_path<K, KFULL>(a, src, global_world(a, env), L, slow_mask, c);
+    GridSource again;
+    again.spv = spv;
+    again.orig = sidx;
+    again.cell_start = cell_start;
+    again.gp = *gpp;
+    again.env = env;
+    again.env_n0 = env * a.N;
+    again.self = j;
+    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), again, global_world(a, env), L, slow_mask, c.p, c.v, c.pref), c);
   }
   agent_back<POLICY>(a, env, la, g, estep, c);
 }

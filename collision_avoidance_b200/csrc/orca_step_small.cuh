@@ -510,10 +510,33 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
 // the warp that take this path together.  `scratch` = the agent's own (now dead) line column, used
 // by the neighbor search as candidate buffer.  Leaves c.overflow set only if even this capacity
 // was exceeded (the statistic the shells turn into an error).
+// Everything crosses the call BY VALUE: a reference to the kernel's AgentCarry, neighbor source or
+// parameter block would force those into local memory for the whole (hot) kernel.
+struct SlowParams {
+  int k;
+  float nd_sq, inv_th, inv_tho, inv_dt, radius, vmax, obst_range_sq;
+};
+struct SlowResult {
+  float2 nv;
+  int n, n_obst, fail;
+  unsigned collisions;
+  bool overflow;
+};
+ORCA_HD SlowParams slow_params(const StepArgs& a) {
+  SlowParams q;
+  q.k = a.k;
+  q.nd_sq = a.nd_sq;
+  q.inv_th = a.inv_th;
+  q.inv_tho = a.inv_tho;
+  q.inv_dt = a.inv_dt;
+  q.radius = a.radius;
+  q.vmax = a.vmax;
+  q.obst_range_sq = a.obst_range_sq;
+  return q;
+}
 template <int K, bool KFULL, class Src>
-ORCA_HD_NOINLINE void agent_slow_path(const StepArgs& a, const Src& src, const ObstacleWorld& W, const Lines scratch,
-                                      const unsigned mask, AgentCarry& c) {
-  const float2 p = c.p, v = c.v;
+ORCA_HD_NOINLINE SlowResult agent_slow_path(const SlowParams a, const Src src, const ObstacleWorld W, const Lines scratch,
+                                            const unsigned mask, const float2 p, const float2 v, const float2 pref) {
   bool overflow = false;
   float od[ORCA_SLOW_MAX_OBST];
   int oid[ORCA_SLOW_MAX_OBST];
@@ -539,12 +562,25 @@ ORCA_HD_NOINLINE void agent_slow_path(const StepArgs& a, const Src& src, const O
       collisions += hit ? 1u : 0u;
     }
   }
-  c.n = n;
-  c.n_obst = n_obst;
-  c.collisions = collisions;
-  c.overflow = overflow;
-  c.fail = lp2(mask, true, L, n, a.vmax, c.pref, false, c.nv);
-  lp3(mask, c.fail < n, L, n, n_obst, c.fail, a.vmax, c.nv);
+  SlowResult r;
+  r.n = n;
+  r.n_obst = n_obst;
+  r.collisions = collisions;
+  r.overflow = overflow;
+  r.nv = v2(0.f, 0.f);
+  r.fail = lp2(mask, true, L, n, a.vmax, pref, false, r.nv);
+  float2 nv = r.nv;
+  lp3(mask, r.fail < n, L, n, n_obst, r.fail, a.vmax, nv);
+  r.nv = nv;
+  return r;
+}
+ORCA_HD void apply_slow_result(const SlowResult& r, AgentCarry& c) {
+  c.nv = r.nv;
+  c.n = r.n;
+  c.n_obst = r.n_obst;
+  c.fail = r.fail;
+  c.collisions = r.collisions;
+  c.overflow = r.overflow;
 }
 
 // Back half: Agent::update + reward + bandit update + done test, with c.nv final.
@@ -632,7 +668,7 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
   c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];
   if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c)) return;
   if (c.overflow)
-    agent_slow_path<K, KFULL>(a, src, global_world(a, env), L, warp_mask, c);
+    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), src, global_world(a, env), L, warp_mask, c.p, c.v, c.pref), c);
   else
     lp3(warp_mask, c.fail < c.n, L, c.n, c.n_obst, c.fail, a.vmax, c.nv);
   agent_back<POLICY>(a, env, la, g, estep, c);
@@ -894,11 +930,9 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   TileSource src;
   const bool tile_grid = a.tile_grid_inv_cell > 0.f;  // uniform over the grid
   if (tile_grid) build_tile_grid(a, s_nv, valid, le, la, c.p, src);
-  ObstacleWorld W;
-  W.n_nodes = 0;
   c.overflow = false;
   if (valid) {
-    W = global_world(a, env);
+    ObstacleWorld W = global_world(a, env);
     if (slots > 0) {
       const int off = le * a.vert_stride;  // 0 for a shared world
       W.vert_pd = s_world + off;
@@ -921,10 +955,18 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
   if (!alive) return;
   c.nv = s_nv[tid];
   if (c.overflow) {  // rare: more obstacle edges / lines than the fast path holds
+    // Everything the slow path needs is rebuilt HERE from scalars (a plain scan of the env's tile --
+    // it yields the same list as the in-block grid -- and the obstacle tables in global memory), so
+    // that nothing of the hot path above has to live in local memory for the sake of this call.
     Lines L;
     L.base = s_lines + tid;
     L.stride = tpb;
-    agent_slow_path<K, KFULL>(a, src, W, L, slow_mask, c);
+    TileSource scan;
+    scan.env_pos = s_pos + le * N;
+    scan.env_vel = s_vel + le * N;
+    scan.n = N;
+    scan.self = la;
+    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), scan, global_world(a, env), L, slow_mask, c.p, c.v, c.pref), c);
   }
   agent_back<POLICY>(a, env, la, g, estep, c);
 }
