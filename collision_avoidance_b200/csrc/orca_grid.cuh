@@ -42,11 +42,22 @@ struct GridParams {
   int ncells;  // E * W * H
 };
 
-// Cell size: neighbor_dist plus 0.1 %.  The margin absorbs the rounding of (x - origin) * inv_cell
-// (about 1.2e-7 relative, i.e. < 1e-3 cells up to ~8000 cells per side), so two agents closer than
-// neighbor_dist always land at most one cell apart.  Exactly neighbor_dist (inv_cell = 0.2f is a
-// hair above 1/5) would let pairs at 4.9999999 fall two cells apart.
-ORCA_HD float grid_cell_size(float neighbor_dist) { return (neighbor_dist > 0.f ? neighbor_dist : 1.f) * 1.001f; }
+// Cell size: neighbor_dist / kGridReach (plus 0.1 %), searched kGridReach cells out in every direction.
+// The 0.1 % absorbs the rounding of (x - origin) * inv_cell (about 1.2e-7 relative, i.e. < 1e-3 cells
+// up to ~8000 cells per side), so two agents closer than neighbor_dist always land at most kGridReach
+// cells apart; exactly neighbor_dist (inv_cell = 0.2f is a hair above 1/5) would let pairs at
+// 4.9999999 fall one cell too far.  The search skips rows and columns of cells whose gap to the agent
+// exceeds the list's CURRENT k-th distance (with a margin of kGapMargin cells for the same rounding).
+// Measured, config 5: reach 1 (cells of nd, 3 x 3) 457 us; reach 2 (cells of nd / 2, 5 x 5 with
+// pruning: 30 instead of 56 candidates per agent) 464 us -- the candidate walk is warp-synchronous
+// (its length is the longest lane's), and the insertions, which dominate, depend on the threshold, not
+// on how many candidates are looked at.
+#ifndef ORCA_GRID_REACH
+#define ORCA_GRID_REACH 1
+#endif
+constexpr int kGridReach = ORCA_GRID_REACH;  // cells searched on each side of the agent's own
+constexpr float kGapMargin = 4.0e-3f;        // cells
+ORCA_HD float grid_cell_size(float neighbor_dist) { return (neighbor_dist > 0.f ? neighbor_dist : 1.f) * (1.001f / kGridReach); }
 
 #if defined(__CUDACC__)
 struct GridScratch {
@@ -109,8 +120,12 @@ struct GridSource {
 
   template <class NK>
   ORCA_HD void gather(NK& nk, float2 p, const Lines& scratch, int scratch_slots, unsigned mask) const {
+    // cell coordinates as floats: same expression as cell_coord, so "agent q is in cell c" means
+    // floor(f(q)) == c for exactly this f
+    const float fx = (p.x - gp.origin_x) * gp.inv_cell, fy = (p.y - gp.origin_y) * gp.inv_cell;
     const int cx = cell_coord(p.x, gp.origin_x, gp.inv_cell, gp.W);
     const int cy = cell_coord(p.y, gp.origin_y, gp.inv_cell, gp.H);
+    const float inv_cell_sq = gp.inv_cell * gp.inv_cell;
     const int base = env * gp.W * gp.H;
     Before before;
     before.orig = orig;
@@ -120,19 +135,43 @@ struct GridSource {
     buf.cap = 2 * scratch_slots;  // two (distSq, id) entries per 16-byte line slot
     buf.cnt = 0;
     auto insert = [&nk, &before](float d, int id) { nk.offer_ranked(d, id, before); };
-    const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < gp.W ? cx + 1 : gp.W - 1;
-    // three rows of cells; the cells (x0..x1, row) are consecutive keys, i.e. one contiguous range
-    // of the sorted arrays.  Lanes walk their own ranges but vote together on every iteration.
-    // The agent's own row goes first: the nearest candidates tighten the threshold early, so fewer of
-    // the later ones are parked and inserted (the list itself does not depend on the visiting order).
-    // (Own cell first, then the rest -- five runs instead of three -- measured slower: 601 vs 575 us.)
+    // 2 * kGridReach + 1 rows of cells, the agent's own first, then outwards: the nearest candidates
+    // tighten the threshold early (the list itself does not depend on the visiting order).  The cells
+    // (x0..x1, row) have consecutive keys, i.e. they are ONE contiguous range of the sorted arrays;
+    // lanes walk their own ranges but vote together on every iteration.
+    // A row is skipped, and its column range narrowed, by the gap (in cells, minus a rounding margin)
+    // between the agent and the row / column: an agent binned there cannot be nearer than the gap.
+    // Border cells also hold the agents clamped into them from outside the box, which are farther
+    // still; the agent's OWN row and column are never pruned (it may itself be a clamped one).
 #pragma unroll 1
-    for (int r = 0; r < 3; ++r) {
-      const int yy = cy + (r == 0 ? 0 : (r == 1 ? -1 : 1));
+    for (int r = 0; r < 2 * kGridReach + 1; ++r) {
+      const int dy = (r & 1) ? -((r + 1) >> 1) : (r >> 1);  // 0, -1, +1, -2, +2
+      const int yy = cy + dy;
       int q = 0, last = 0;
       if (yy >= 0 && yy < gp.H) {
-        q = ORCA_LDG(&cell_start[base + yy * gp.W + x0]);
-        last = ORCA_LDG(&cell_start[base + yy * gp.W + x1 + 1]);
+        int x0 = cx - kGridReach > 0 ? cx - kGridReach : 0;
+        int x1 = cx + kGridReach < gp.W ? cx + kGridReach : gp.W - 1;
+        bool visit = true;
+        if (kGridReach > 1) {  // pruning pays only with cells finer than the range (measured: costs 6 us at reach 1)
+          float gy = (dy < 0) ? fy - (float)(yy + 1) : ((dy > 0) ? (float)yy - fy : 0.f);
+          gy = fmaxf(gy - kGapMargin, 0.f);
+          const float rem = nk.thresh() * inv_cell_sq - gy * gy;  // what is left for the column gap, in cells^2
+          visit = rem >= 0.f;
+          while (visit && x0 < cx) {
+            const float gx = fmaxf(fx - (float)(x0 + 1) - kGapMargin, 0.f);
+            if (!(gx * gx > rem)) break;
+            ++x0;
+          }
+          while (visit && x1 > cx) {
+            const float gx = fmaxf((float)x1 - fx - kGapMargin, 0.f);
+            if (!(gx * gx > rem)) break;
+            --x1;
+          }
+        }
+        if (visit) {
+          q = ORCA_LDG(&cell_start[base + yy * gp.W + x0]);
+          last = ORCA_LDG(&cell_start[base + yy * gp.W + x1 + 1]);
+        }
       }
       // the position of the NEXT candidate is fetched while the current one is tested and parked:
       // the load (L1 / L2 latency) is the longest single wait of this loop
@@ -363,23 +402,33 @@ __global__ void __launch_bounds__(kScanThreads) grid_scan_kernel(int* __restrict
   int total;
   const int local = block_exclusive_scan(s, &total);
   const unsigned long long tag = (unsigned long long)epoch << 34;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {  // warp 0 looks back over 32 predecessors at a time
     volatile unsigned long long* st = tile_state;
+    const int lane = threadIdx.x;
+    if (lane == 0 && tile > 0) st[tile] = tag | (1ull << 32) | (unsigned)total;  // aggregate available
     int prefix = 0;
-    if (tile > 0) {
-      st[tile] = tag | (1ull << 32) | (unsigned)total;  // aggregate available
-      for (int p = tile - 1; p >= 0; --p) {
-        unsigned long long w;
+    for (int hi = tile - 1; hi >= 0; hi -= 32) {
+      const int pidx = hi - lane;
+      unsigned long long w = tag | (2ull << 32);  // lanes in front of tile 0: an inclusive prefix of 0
+      if (pidx >= 0) {
         do {
-          w = st[p];
+          w = st[pidx];
         } while ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0ull);
-        prefix += (int)(unsigned)(w & 0xffffffffull);
-        if (((w >> 32) & 3ull) == 2ull) break;  // an inclusive prefix: nothing further back is needed
       }
+      const unsigned incl = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == 2ull);
+      // nearest predecessor with an inclusive prefix: everything nearer contributes its aggregate
+      const int stop = incl ? __ffs((int)incl) - 1 : 31;
+      int v = (lane <= stop) ? (int)(unsigned)(w & 0xffffffffull) : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      prefix += v;
+      if (incl) break;
     }
-    __threadfence();
-    st[tile] = tag | (2ull << 32) | (unsigned)(prefix + total);  // inclusive prefix available
-    s_prefix = prefix;
+    if (lane == 0) {
+      __threadfence();
+      st[tile] = tag | (2ull << 32) | (unsigned)(prefix + total);  // inclusive prefix available
+      s_prefix = prefix;
+    }
   }
   __syncthreads();
   int off = local + s_prefix;
