@@ -377,24 +377,38 @@ def run_ours(args, cfg_name, cfg):
     # ---- end-to-end region: host buffers through the C ABI, same episode phase ----------------
     e2e_steps = max(3, args.steps)
     bytes_state = E * N * 8
+    e2e_min = None
     if wl.alan is None:
         pos_h = sim.pos.cpu().pin_memory()
         vel_h = sim.vel.cpu().pin_memory()
         goal_h = wl.goal_tensor().cpu().pin_memory()
-        sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=1)
-        for _ in range(8):  # untimed: the library times both of its routes (direct / staged) on its first six steady calls and keeps the faster
-            sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            # per step: goals host->device (the setAgentPrefVelocity traffic), doStep, then
-            # positions + velocities device->host (the getAgentPosition/Velocity traffic)
-            sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
-        barrier()
-        e2e_dt = time.perf_counter() - t0
+
+        def host_region(vel_out, aux_unchanged):
+            sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=1, aux_unchanged=aux_unchanged)
+            for _ in range(8):  # untimed: the library times both of its routes (direct / staged) on its first six steady calls and keeps the faster
+                sim.step_host(pos_h, vel_out, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1, aux_unchanged=aux_unchanged)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                sim.step_host(pos_h, vel_out, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1, aux_unchanged=aux_unchanged)
+            barrier()
+            return time.perf_counter() - t0
+
+        # headline e2e: per step the goals go host->device (the setAgentPrefVelocity traffic), doStep,
+        # then positions + velocities come device->host (the getAgentPosition/Velocity traffic)
+        e2e_dt = host_region(vel_h, False)
         h2d, d2h = bytes_state, 2 * bytes_state
-        e2e_api = ("BatchedRVOSimulator.step_host -> orca_step_host (pinned host buffers; the library keeps the faster of its "
+        e2e_api = ("BatchedRVOSimulator.step_host -> orca_step_host_ex (pinned host buffers; the library keeps the faster of its "
                    "two routes: kernel reads/writes the mapped host buffers directly, or chunked upload | step | download over streams)")
+        # the least a host-side run_sim(mode=0) loop needs per step: the new positions (the goals are
+        # static, velocities are never read by that loop: ALAN_true.py:483-495,547-566,631-633)
+        min_dt = host_region(None, True)
+        tm = torch.tensor([min_dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_min = {"value": world * E * N * e2e_steps / float(tm.item()), "unit": UNIT, "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": bytes_state,
+                   "api": "orca_step_host_ex(vel_host = NULL, ORCA_HOST_AUX_UNCHANGED): positions-only write-back, goal buffer not re-read"}
     else:
         # ALAN has no per-step host INPUT (actions are drawn on the device); what a host-side caller
         # reads back every step is the reward, the chosen action and the done flags
@@ -418,6 +432,31 @@ def run_ours(args, cfg_name, cfg):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * E * N * e2e_steps / float(te.item())
+
+    # ---- host-link probe: what the box's host memory / PCIe complex carries when every rank moves
+    # the e2e byte pattern (8 B in + 16 B out per agent) with NO compute: the ceiling of `e2e` -----
+    probe_in = torch.empty(E * N * 2, dtype=torch.float32).pin_memory()
+    probe_out = torch.empty(E * N * 4, dtype=torch.float32).pin_memory()
+    d_in, d_out = torch.empty(E * N * 2, device=dev), torch.empty(E * N * 4, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    probe_iters = 20
+
+    def probe_once():
+        with torch.cuda.stream(s_in):
+            d_in.copy_(probe_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            probe_out.copy_(d_out, non_blocking=True)
+    for _ in range(3):
+        probe_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(probe_iters):
+        probe_once()
+    barrier()
+    tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    probe_gbs = world * (probe_in.numel() + probe_out.numel()) * 4 * probe_iters / float(tp.item()) / 1e9
 
     # ---- cost profile over the episode (rank 0, untimed in the headline) -----------------------
     by_phase, trace_mean = None, None
@@ -471,6 +510,11 @@ def run_ours(args, cfg_name, cfg):
                          "issue_profile": issue_profile},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": e2e_api},
+            "e2e_min_traffic": e2e_min,
+            "host_link_probe": {"aggregate_GBps": probe_gbs, "bytes_per_agent_step": 24,
+                                "e2e_ceiling": probe_gbs * 1e9 / 24.0,
+                                "how": "every rank copies 8 B/agent host->device and 16 B/agent device->host (pinned, two streams, "
+                                       "no kernel) at the same time; e2e cannot exceed this on this host"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "host_affinity": {"rank0_cores": len(cores) if cores else None,

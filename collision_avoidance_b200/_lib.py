@@ -26,6 +26,8 @@ DONE_NONE, DONE_GOAL_RADIUS, DONE_X_BELOW, DONE_GOAL_RADIUS_DEFERRED = 0, 1, 2, 
 STAT_AGENT_STEPS, STAT_FINISHED, STAT_COLLISIONS, STAT_LP3_CALLS, STAT_OVERFLOW = 0, 1, 2, 3, 4
 STAT_SUM_ARRIVAL, STAT_SUM_ARRIVAL2, STAT_SUM_REWARD, STAT_COUNT = 5, 6, 7, 8
 
+HOST_UPLOAD_STATE, HOST_AUX_UNCHANGED = 1, 2
+
 MAX_OBST_NEIGHBORS = 16
 MAX_ACTIONS = 16
 
@@ -33,7 +35,7 @@ MAX_ACTIONS = 16
 EXPORTED_SYMBOLS = (
     "orca_abi_version", "orca_last_error", "orca_create", "orca_destroy", "orca_get_params",
     "orca_set_obstacles", "orca_obstacle_vertex_count", "orca_get_obstacle_vertices",
-    "orca_step", "orca_env_step", "orca_env_step_many", "orca_neighbors", "orca_observe", "orca_step_host", "orca_policy_mlp", "orca_policy_mlp_fp32", "orca_launch_count",
+    "orca_step", "orca_env_step", "orca_env_step_many", "orca_neighbors", "orca_observe", "orca_step_host", "orca_step_host_ex", "orca_policy_mlp", "orca_policy_mlp_fp32", "orca_launch_count",
 )
 
 
@@ -134,6 +136,8 @@ def load() -> ctypes.CDLL:
     L.orca_neighbors.argtypes = [hp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.orca_observe.argtypes = [hp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, i, i, _vp, _vp]
     L.orca_step_host.argtypes = [hp, _vp, _vp, _vp, i, i, i]
+    L.orca_step_host_ex.argtypes = [hp, _vp, _vp, _vp, i, i, i]
+    L.orca_step_host_ex.restype = i
     L.orca_policy_mlp.argtypes = [hp, _vp, ctypes.c_int64, ctypes.POINTER(OrcaMlpWeights), _vp, _vp]
     L.orca_policy_mlp_fp32.argtypes = [hp, _vp, ctypes.c_int64, ctypes.POINTER(OrcaMlpWeights), _vp, _vp]
     L.orca_launch_count.argtypes = [hp]

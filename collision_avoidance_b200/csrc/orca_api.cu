@@ -70,9 +70,9 @@ struct HostGraphKey {
   const void* pos;
   const void* vel;
   const void* aux;
-  int policy, upload_state, steps, chunks;
+  int policy, flags, steps, chunks;
   bool operator==(const HostGraphKey& o) const {
-    return pos == o.pos && vel == o.vel && aux == o.aux && policy == o.policy && upload_state == o.upload_state &&
+    return pos == o.pos && vel == o.vel && aux == o.aux && policy == o.policy && flags == o.flags &&
            steps == o.steps && chunks == o.chunks;
   }
 };
@@ -97,6 +97,7 @@ struct OrcaSim {
   float2* d_vel = nullptr;
   float2* d_aux = nullptr;
   bool host_state_valid = false;  // d_pos / d_vel hold a state uploaded by an orca_step_host(upload_state = 1) call
+  const void* host_aux_src = nullptr;  // host buffer whose content d_aux currently mirrors (ORCA_HOST_AUX_UNCHANGED)
   cudaStream_t host_streams[kHostChunksMax] = {};
   cudaEvent_t host_fork = nullptr;
   cudaEvent_t host_join[kHostChunksMax] = {};
@@ -574,10 +575,11 @@ namespace {
 // One orca_step_host call over the route asked for: direct (kernel reads / writes the mapped host
 // buffers) when `allow_direct` and the buffers are mapped, else staged copies.
 int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* pref_or_goal_host, int policy,
-                    int upload_state, int steps, bool allow_direct) {
+                    int flags, int steps, bool allow_direct) {
   if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
-  if (pos_host == nullptr || vel_host == nullptr || pref_or_goal_host == nullptr)
-    return fail(ORCA_ERR_INVALID, "null host buffer");
+  const int upload_state = (flags & ORCA_HOST_UPLOAD_STATE) ? 1 : 0;
+  if (pos_host == nullptr || pref_or_goal_host == nullptr) return fail(ORCA_ERR_INVALID, "null host buffer");
+  if (vel_host == nullptr && upload_state) return fail(ORCA_ERR_INVALID, "uploading the state needs vel_host");
   if (policy != ORCA_POLICY_EXTERNAL && policy != ORCA_POLICY_GOAL)
     return fail(ORCA_ERR_INVALID, "orca_step_host supports the EXTERNAL and GOAL policies");
   if (steps < 1) return fail(ORCA_ERR_INVALID, "steps must be >= 1");
@@ -587,6 +589,10 @@ int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* p
   int rc = ensure_host_staging(s);
   if (rc != ORCA_OK) return rc;
   if (upload_state) s->host_state_valid = true;
+  // ORCA_HOST_AUX_UNCHANGED: the caller promises that the goal / pref buffer holds what it held at the
+  // previous call with the same pointer; its device copy is reused and nothing is read from the host
+  const bool aux_cached = (flags & ORCA_HOST_AUX_UNCHANGED) != 0 && s->host_aux_src == pref_or_goal_host;
+  const bool want_vel = vel_host != nullptr;
   // ---- direct path: the host buffers are pinned and mapped -------------------------------------
   // The step kernel itself reads the goals / preferred velocities from the caller's buffer and
   // writes the new positions and velocities into the caller's buffers (as well as into the
@@ -596,7 +602,7 @@ int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* p
   if (tile_path && allow_direct) {
     void *m_pos = nullptr, *m_vel = nullptr, *m_aux = nullptr;
     const bool mapped = cudaHostGetDevicePointer(&m_pos, pos_host, 0) == cudaSuccess &&
-                        cudaHostGetDevicePointer(&m_vel, vel_host, 0) == cudaSuccess &&
+                        (!want_vel || cudaHostGetDevicePointer(&m_vel, vel_host, 0) == cudaSuccess) &&
                         cudaHostGetDevicePointer(&m_aux, const_cast<float*>(pref_or_goal_host), 0) == cudaSuccess;
     if (!mapped) {
       cudaGetLastError();  // pageable buffers: clear the error, take the staged path below
@@ -612,9 +618,14 @@ int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* p
       a.pos = s->d_pos;
       a.vel = s->d_vel;
       const float2* aux = static_cast<const float2*>(m_aux);
-      if (steps > 1) {  // read every step: bring it over once
+      if (aux_cached) {
+        aux = s->d_aux;
+      } else if (steps > 1 || (flags & ORCA_HOST_AUX_UNCHANGED)) {  // read every step / reused by later calls: bring it over once
         CUDA_TRY(cudaMemcpyAsync(s->d_aux, pref_or_goal_host, bytes, cudaMemcpyHostToDevice, st));
         aux = s->d_aux;
+        s->host_aux_src = pref_or_goal_host;
+      } else {
+        s->host_aux_src = nullptr;
       }
       if (policy == ORCA_POLICY_EXTERNAL)
         a.pref = aux;
@@ -623,7 +634,7 @@ int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* p
       for (int t = 0; t < steps; ++t) {
         if (t == steps - 1) {
           a.pos_mirror = static_cast<float2*>(m_pos);
-          a.vel_mirror = static_cast<float2*>(m_vel);
+          a.vel_mirror = want_vel ? static_cast<float2*>(m_vel) : nullptr;
         }
         rc = launch_step(s, a, policy, st);
         if (rc != ORCA_OK) return rc;
@@ -669,7 +680,7 @@ int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* p
     for (int c = 1; c <= chunks; ++c) bound[c] = std::max(bound[c], std::min(s->E, bound[c - 1] + 1));  // no empty chunk
     bound[chunks] = s->E;
   }
-  HostGraphKey key{pos_host, vel_host, pref_or_goal_host, policy, upload_state, steps, chunks};
+  HostGraphKey key{pos_host, vel_host, pref_or_goal_host, policy, flags | (aux_cached ? 0x100 : 0), steps, chunks};
   const bool use_graph = tile_path && std::getenv("ORCA_B200_HOST_NO_GRAPH") == nullptr;
   if (use_graph && s->host_graph_exec != nullptr && !(key == s->host_graph_key)) {
     cudaGraphExecDestroy(s->host_graph_exec);
@@ -702,13 +713,14 @@ int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* p
         ce = cudaMemcpyAsync(s->d_pos + off, pos_host + 2 * off, bytes, cudaMemcpyHostToDevice, st);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(s->d_vel + off, vel_host + 2 * off, bytes, cudaMemcpyHostToDevice, st);
       }
-      if (ce == cudaSuccess) ce = cudaMemcpyAsync(s->d_aux + off, pref_or_goal_host + 2 * off, bytes, cudaMemcpyHostToDevice, st);
+      if (ce == cudaSuccess && !aux_cached)
+        ce = cudaMemcpyAsync(s->d_aux + off, pref_or_goal_host + 2 * off, bytes, cudaMemcpyHostToDevice, st);
       orca::StepArgs ac = a;
       ac.env_base = e0;
       ac.E = e1;
       for (int t = 0; t < steps && rc == ORCA_OK && ce == cudaSuccess; ++t) rc = launch_step(s, ac, policy, st);
       if (ce == cudaSuccess) ce = cudaMemcpyAsync(pos_host + 2 * off, s->d_pos + off, bytes, cudaMemcpyDeviceToHost, st);
-      if (ce == cudaSuccess) ce = cudaMemcpyAsync(vel_host + 2 * off, s->d_vel + off, bytes, cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess && want_vel) ce = cudaMemcpyAsync(vel_host + 2 * off, s->d_vel + off, bytes, cudaMemcpyDeviceToHost, st);
       if (use_graph && c > 0 && ce == cudaSuccess) {
         ce = cudaEventRecord(s->host_join[c], st);
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(root, s->host_join[c], 0);
@@ -738,12 +750,14 @@ int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* p
       if (rc != ORCA_OK) return rc;
       if (ce != cudaSuccess) return fail(ORCA_ERR_CUDA, "host step failed: %s", cudaGetErrorString(ce));
       for (int c = 0; c < chunks; ++c) CUDA_TRY(cudaStreamSynchronize(s->host_streams[c]));
+      s->host_aux_src = pref_or_goal_host;
       return ORCA_OK;
     }
   }
   CUDA_TRY(cudaGraphLaunch(s->host_graph_exec, root));
   s->launches += s->host_graph_launches;
   CUDA_TRY(cudaStreamSynchronize(root));
+  s->host_aux_src = pref_or_goal_host;  // the staged route always leaves a device copy of it behind
   return ORCA_OK;
 }
 
@@ -751,17 +765,19 @@ int step_host_route(OrcaSim* s, float* pos_host, float* vel_host, const float* p
 
 extern "C" {
 
-int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pref_or_goal_host, int policy,
-                   int upload_state, int steps) {
+int orca_step_host_ex(OrcaSim* s, float* pos_host, float* vel_host, const float* pref_or_goal_host, int policy, int flags,
+                      int steps) {
   if (s == nullptr) return fail(ORCA_ERR_INVALID, "null handle");
+  if (flags & ~(ORCA_HOST_UPLOAD_STATE | ORCA_HOST_AUX_UNCHANGED)) return fail(ORCA_ERR_INVALID, "unknown host-step flags 0x%x", flags);
   const bool may_direct = std::getenv("ORCA_B200_HOST_NO_MAPPED") == nullptr;
   // Which route is faster depends on the host (PCIe write efficiency of GPU stores vs copy-engine
   // bursts; measured 0.39 vs 0.45 ms on one box, 0.51 vs 0.45 ms on another).  Both give the same
   // bits, so steady-state calls (same buffers, one step, no state upload) time each route three
   // times and keep the faster one.
-  const bool steady = may_direct && upload_state == 0 && steps == 1 && std::getenv("ORCA_B200_HOST_NO_AUTOTUNE") == nullptr;
-  if (!steady) return step_host_route(s, pos_host, vel_host, pref_or_goal_host, policy, upload_state, steps, may_direct);
-  HostGraphKey key{pos_host, vel_host, pref_or_goal_host, policy, 0, 1, 0};
+  const bool steady = may_direct && !(flags & ORCA_HOST_UPLOAD_STATE) && steps == 1 &&
+                      std::getenv("ORCA_B200_HOST_NO_AUTOTUNE") == nullptr;
+  if (!steady) return step_host_route(s, pos_host, vel_host, pref_or_goal_host, policy, flags, steps, may_direct);
+  HostGraphKey key{pos_host, vel_host, pref_or_goal_host, policy, flags, 1, 0};
   if (!(key == s->tune_key)) {
     s->tune_key = key;
     s->tune_calls = 0;
@@ -777,7 +793,7 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
     direct = s->tune_ms[0] <= s->tune_ms[1];
   }
   const auto t0 = std::chrono::steady_clock::now();
-  const int rc = step_host_route(s, pos_host, vel_host, pref_or_goal_host, policy, upload_state, steps, direct);
+  const int rc = step_host_route(s, pos_host, vel_host, pref_or_goal_host, policy, flags, steps, direct);
   if (s->tune_calls < 2 * kTunePerRoute) {
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     const int route = s->tune_calls / kTunePerRoute, nth = s->tune_calls % kTunePerRoute;
@@ -789,6 +805,12 @@ int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pr
                    s->tune_ms[0] <= s->tune_ms[1] ? "direct" : "staged");
   }
   return rc;
+}
+
+int orca_step_host(OrcaSim* s, float* pos_host, float* vel_host, const float* pref_or_goal_host, int policy,
+                   int upload_state, int steps) {
+  if (vel_host == nullptr) return fail(ORCA_ERR_INVALID, "null host buffer");
+  return orca_step_host_ex(s, pos_host, vel_host, pref_or_goal_host, policy, upload_state ? ORCA_HOST_UPLOAD_STATE : 0, steps);
 }
 
 }  // extern "C"

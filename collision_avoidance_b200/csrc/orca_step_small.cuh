@@ -595,10 +595,8 @@ ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const in
   const float2 p = add(c.p, mul(a.dt, v));  // position += velocity * timeStep
   a.pos[g] = p;
   a.vel[g] = v;
-  if (a.pos_mirror != nullptr) {
-    a.pos_mirror[g] = p;
-    a.vel_mirror[g] = v;
-  }
+  if (a.pos_mirror != nullptr) a.pos_mirror[g] = p;
+  if (a.vel_mirror != nullptr) a.vel_mirror[g] = v;
 
   // ---------------- reward / bandit update ----------------
   if (POLICY == POLICY_RL || POLICY == POLICY_ALAN) {

@@ -274,15 +274,20 @@ class BatchedRVOSimulator:
         return obs
 
     # ------------------------------------------------------------------ host-buffer (e2e) path
-    def step_host(self, pos_host: torch.Tensor, vel_host: torch.Tensor, pref_or_goal_host: torch.Tensor,
-                  policy: int = _lib.POLICY_EXTERNAL, upload_state: bool = True, steps: int = 1):
-        """orca_step_host: host buffers in, host buffers out, copies inside the call."""
+    def step_host(self, pos_host: torch.Tensor, vel_host: Optional[torch.Tensor], pref_or_goal_host: torch.Tensor,
+                  policy: int = _lib.POLICY_EXTERNAL, upload_state: bool = True, steps: int = 1,
+                  aux_unchanged: bool = False):
+        """orca_step_host_ex: host buffers in, host buffers out, copies inside the call.
+        ``vel_host=None`` writes only the positions back; ``aux_unchanged`` promises that the goal /
+        pref buffer still holds what it held at the previous call (nothing is read from the host)."""
         for t, name in ((pos_host, "pos_host"), (vel_host, "vel_host"), (pref_or_goal_host, "pref_or_goal_host")):
+            if t is None and name == "vel_host":
+                continue
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != self.pos.numel():
                 raise ValueError(f"{name} must be a contiguous CPU float32 tensor with {self.pos.numel()} elements")
-        _lib.check(self._L.orca_step_host(self._h, pos_host.data_ptr(), vel_host.data_ptr(),
-                                          pref_or_goal_host.data_ptr(), int(policy), int(bool(upload_state)),
-                                          int(steps)))
+        flags = (_lib.HOST_UPLOAD_STATE if upload_state else 0) | (_lib.HOST_AUX_UNCHANGED if aux_unchanged else 0)
+        _lib.check(self._L.orca_step_host_ex(self._h, pos_host.data_ptr(), None if vel_host is None else vel_host.data_ptr(),
+                                             pref_or_goal_host.data_ptr(), int(policy), int(flags), int(steps)))
 
     def launch_count(self) -> int:
         return int(self._L.orca_launch_count(self._h))

@@ -234,6 +234,19 @@ int orca_policy_mlp_fp32(OrcaSim* sim, const float* obs_dev, int64_t rows, const
  *     graph while the arguments stay the same. */
 int orca_step_host(OrcaSim* sim, float* pos_host, float* vel_host, const float* pref_or_goal_host, int policy,
                    int upload_state, int steps);
+/* The same with the per-step host traffic under the caller's control:
+ *   ORCA_HOST_UPLOAD_STATE   take pos / vel from the host buffers first (= upload_state above)
+ *   ORCA_HOST_AUX_UNCHANGED  the goal / pref buffer holds what it held at the previous call with the same
+ *                            pointer: its device copy is reused, nothing is read from the host.  Goals are
+ *                            static under ORCA_POLICY_GOAL, and the reference's orca_step loop
+ *                            (ALAN_true.py:631-633) writes no per-step input either.
+ * vel_host may be NULL: only the positions are written back -- all that loop reads per step
+ * (getAgentPosition in update_pref_vel / done_test, ALAN_true.py:490,553).  Returns ORCA_ERR_STATE when the
+ * state was never uploaded. */
+#define ORCA_HOST_UPLOAD_STATE 1
+#define ORCA_HOST_AUX_UNCHANGED 2
+int orca_step_host_ex(OrcaSim* sim, float* pos_host, float* vel_host, const float* pref_or_goal_host, int policy,
+                      int flags, int steps);
 
 /* Number of kernels launched through this handle so far (bench.py's gpu_launches). */
 int64_t orca_launch_count(const OrcaSim* sim);

@@ -265,3 +265,36 @@ def test_handles_on_two_devices_in_one_process():
             sim.env_step(policy=_lib.POLICY_GOAL, goal=goal)
         outs.append(sim.pos.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("mode", ["mapped", "staged"])
+def test_host_entry_point_reduced_traffic_variants(monkeypatch, mode):
+    """orca_step_host_ex: positions-only write-back (vel_host = NULL) and ORCA_HOST_AUX_UNCHANGED (the
+    goal buffer is not re-read) give the bits of the full-traffic call on both routes; a changed goal
+    buffer is picked up again as soon as the flag is dropped; stepping before any state upload is
+    ORCA_ERR_STATE, not garbage."""
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    if mode == "staged":
+        monkeypatch.setenv("ORCA_B200_HOST_NO_MAPPED", "1")
+    scn = scenarios.circle(70, 16, seed=91)
+    E, N = scn.num_envs, scn.agents_per_env
+    full, lean = _mk(scn), _mk(scn)
+    pin = lambda x: torch.from_numpy(x.copy()).pin_memory()   # noqa: E731
+    pf, vf, gf = pin(scn.pos), pin(scn.vel), pin(scn.goal)
+    pl, vl, gl = pin(scn.pos), pin(scn.vel), pin(scn.goal)
+    with pytest.raises(RuntimeError):
+        lean.step_host(pl, None, gl, policy=_lib.POLICY_GOAL, upload_state=False)
+    full.step_host(pf, vf, gf, policy=_lib.POLICY_GOAL, upload_state=True)
+    lean.step_host(pl, vl, gl, policy=_lib.POLICY_GOAL, upload_state=True, aux_unchanged=True)
+    for t in range(12):
+        full.step_host(pf, vf, gf, policy=_lib.POLICY_GOAL, upload_state=False)
+        lean.step_host(pl, None, gl, policy=_lib.POLICY_GOAL, upload_state=False, aux_unchanged=True)
+        assert torch.equal(pf, pl), t
+    assert not torch.equal(vf, vl)                  # the lean call never wrote velocities back ...
+    # ... but its device state carries them: a full call afterwards returns the same velocities
+    gf.copy_(torch.from_numpy(scn.pos))             # new goals (everybody walks home): flag dropped -> re-read
+    gl.copy_(torch.from_numpy(scn.pos))
+    full.step_host(pf, vf, gf, policy=_lib.POLICY_GOAL, upload_state=False)
+    lean.step_host(pl, vl, gl, policy=_lib.POLICY_GOAL, upload_state=False)
+    assert torch.equal(pf, pl) and torch.equal(vf, vl)
