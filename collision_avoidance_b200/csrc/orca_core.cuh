@@ -52,6 +52,17 @@ extern long long g_orca_counters[16];
 #define ORCA_COUNT(slot, n) ((void)0)
 #endif
 
+// -DORCA_DEBUG_CHECKS: device-side bounds / ownership asserts on every re-used piece of shared memory
+// (line slots <-> candidate buffer, LP3 queue <-> in-block grid, dead line columns <-> LP3 programme).
+// compute-sanitizer is not available on the GPU pool this was developed on; a build with these checks
+// runs the small-shape smoke (tools/sanitize_smoke.py) and the parity tests instead (profiles/README.md).
+#if defined(ORCA_DEBUG_CHECKS)
+#include <assert.h>
+#define ORCA_DCHECK(cond) assert(cond)
+#else
+#define ORCA_DCHECK(cond) ((void)0)
+#endif
+
 namespace orca {
 
 constexpr float kEps = 0.00001f;  // RVO_EPSILON
@@ -676,6 +687,7 @@ struct CandidateBuffer {
   int cnt;
   ORCA_HD float2* entry(int r) const { return reinterpret_cast<float2*>(&base[(r >> 1) * stride]) + (r & 1); }
   ORCA_HD void push(float d, int id) {
+    ORCA_DCHECK(cnt >= 0 && cnt < cap);
     *entry(cnt) = v2(d, bits_to_float(id));  // (distSq, id bits)
     ++cnt;
   }
@@ -926,6 +938,7 @@ ORCA_HD int obstacle_lines(const ObstacleWorld& W, float2 p, float2 vel, float r
     }
     if (emit) {
       if (nl < MAXL) {
+        ORCA_DCHECK(nl >= 0);
         L.set(nl++, out_pt, out_dir);
       } else {
         *overflow = true;

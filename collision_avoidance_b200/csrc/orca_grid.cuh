@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float2* __restr
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T) return;
   const int j = cell_start[key[i]] + slot[i];
+  ORCA_DCHECK(j >= 0 && j < T);
   const float2 p = pos[i], v = vel[i];
   spv[j] = make_float4(p.x, p.y, v.x, v.y);
   sidx[j] = i;

@@ -153,6 +153,7 @@ struct TileSource {
     for (int j = 0; j < M; ++j) {
       const bool in = d[j] < nk.range_sq && r[j] < nk.k;  // k <= 16: the rank fits the 16-byte slot
       cnt += in ? 1 : 0;
+      ORCA_DCHECK(!in || (r[j] >= 0 && r[j] < 16));
       if (in) slot[r[j]] = (unsigned char)j;
     }
     nk.set_sorted_ids(*reinterpret_cast<const uint4*>(scratch.base), cnt);
@@ -204,6 +205,7 @@ struct TileSource {
           for (int u = 0; u < 2; ++u) {
             if (q < last) {
               const int j = sorted[q];
+              ORCA_DCHECK(q >= 0 && q < n && j >= 0 && j < n);
               if (j != self) {
                 const float d = abs_sq(sub(p, env_pos[j]));
                 if (d <= nk.thresh()) buf.push(d, j);
@@ -436,6 +438,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
         w2 = (w2 >> 8) | (w3 << 24);
         w3 >>= 8;
         bool hit;
+        ORCA_DCHECK(n < K + ORCA_MAX_OBST_LINES);
         const float4 ln = agent_line(p, v, src.pos(j), src.vel(j), cr, a.inv_th, a.inv_dt, &hit);
         L.base[n * L.stride] = ln;
         ++n;
@@ -788,6 +791,15 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
     L.stride = blockDim.x;
     float2 nv = s_nv[owner];
     if ((warp << 5) < nstored) {
+#if defined(ORCA_DEBUG_CHECKS)
+      if (mine) {  // the borrowed column belongs to a thread that is NOT in the LP3 queue, and to nobody else
+        const int col = (int)s_queue[blockDim.x - 1 - tid];
+        assert(col >= 0 && col < (int)blockDim.x && tid < nfree);
+        for (int q = 0; q < total; ++q) assert((int)s_queue[q] != col);
+        for (int q = 0; q < nstored; ++q) assert(q == tid || (int)s_queue[blockDim.x - 1 - q] != col);
+        assert(owner >= 0 && owner < (int)blockDim.x && (meta & 0xff) <= K + ORCA_MAX_OBST_LINES);
+      }
+#endif
       Lines P;
       P.base = s_lines + (mine ? (int)s_queue[blockDim.x - 1 - tid] : tid);
       P.stride = blockDim.x;
@@ -857,6 +869,8 @@ __device__ __forceinline__ void build_tile_grid(const StepArgs& a, void* area, c
     if (lane == 31) start[e * kTileStartStride + kTileCells] = (unsigned short)incl;
   }
   __syncthreads();
+  ORCA_DCHECK(!valid || (start[le * kTileStartStride + ck] + slot < a.N && start[le * kTileStartStride + kTileCells] == a.N));
+  ORCA_DCHECK((char*)(sorted + envs * a.N) - (char*)area <= 14 * (int)blockDim.x + 128);  // the borrowed LP3 queue area
   if (valid) sorted[le * a.N + start[le * kTileStartStride + ck] + slot] = (unsigned char)la;
   __syncthreads();
   src.cell_start = start + le * kTileStartStride;
