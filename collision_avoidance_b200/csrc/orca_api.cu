@@ -188,10 +188,6 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   if (N > 32 && s->p.neighbor_dist > 0.f && std::getenv("ORCA_B200_NO_TILE_GRID") == nullptr)
     args.tile_grid_inv_cell = 1.0f / (s->p.neighbor_dist * 1.001f);
   size_t smem = orca::step_smem_bytes(K, tpb, true, args.world_slots);
-  if (const char* e = std::getenv("ORCA_B200_SMEM_PAD")) {  // dev knob: extra shared memory = fewer resident blocks (occupancy experiments)
-    const long v = std::atol(e);
-    if (v > 0 && smem + (size_t)v <= orca::step_smem_bytes(K, 256, true, 256)) smem += (size_t)v;
-  }
   auto kern = orca::step_small_kernel<K, KFULL, POLICY>;
   // function attributes are per device: one flag per (instantiation, device)
   // (distinct handles may be driven from distinct threads: atomic flags; setting the attribute twice is harmless)
@@ -199,6 +195,13 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   if (s->device >= orca::kMaxDevices || !attr_set[s->device].load(std::memory_order_acquire)) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::step_smem_bytes(K, 256, true, 256)));
     if (s->device < orca::kMaxDevices) attr_set[s->device].store(true, std::memory_order_release);
+  }
+  if (const char* e = std::getenv("ORCA_B200_SMEM_PAD")) {  // dev knob: extra shared memory = fewer resident blocks (occupancy experiments)
+    const long v = std::atol(e);
+    if (v > 0 && smem + (size_t)v <= 227 * 1024) {
+      smem += (size_t)v;
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
   }
   kern<<<blocks, tpb, smem, st>>>(args);
   CUDA_TRY(cudaGetLastError());
