@@ -167,8 +167,8 @@ void fill_common(const OrcaSim* s, orca::StepArgs* a) {
   a->world_slots = 0;
 }
 
-template <int K, bool KFULL, int POLICY>
-int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
+template <int K, bool KFULL, int POLICY, int OL>
+int launch_small_kpo(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   const int N = s->N;
   // 256-thread blocks: whole envs per block (256 / N of them); measured faster than 128 / 64 / 32
   // because the block-level LP3 queue gets denser
@@ -187,13 +187,15 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   args.tile_grid_inv_cell = 0.f;
   if (N > 32 && s->p.neighbor_dist > 0.f && std::getenv("ORCA_B200_NO_TILE_GRID") == nullptr)
     args.tile_grid_inv_cell = 1.0f / (s->p.neighbor_dist * 1.001f);
-  size_t smem = orca::step_smem_bytes(K, tpb, true, args.world_slots);
-  auto kern = orca::step_small_kernel<K, KFULL, POLICY>;
+  size_t smem = orca::step_smem_bytes(K, tpb, true, args.world_slots, OL);
+  auto kern = orca::step_small_kernel<K, KFULL, POLICY, OL>;
   // function attributes are per device: one flag per (instantiation, device)
   // (distinct handles may be driven from distinct threads: atomic flags; setting the attribute twice is harmless)
   static std::atomic<bool> attr_set[orca::kMaxDevices];
   if (s->device >= orca::kMaxDevices || !attr_set[s->device].load(std::memory_order_acquire)) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::step_smem_bytes(K, 256, true, 256)));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)orca::step_smem_bytes(K, 256, true, 256, OL)));
+    // the whole unified L1 as shared memory: the resident-block count is what this kernel lives on
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     if (s->device < orca::kMaxDevices) attr_set[s->device].store(true, std::memory_order_release);
   }
   if (const char* e = std::getenv("ORCA_B200_SMEM_PAD")) {  // dev knob: extra shared memory = fewer resident blocks (occupancy experiments)
@@ -207,6 +209,16 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;
   return ORCA_OK;
+}
+
+template <int K, bool KFULL, int POLICY>
+int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
+  // a world of at most 4 processed vertices (none, or one wall) gives an agent at most 2 obstacle lines:
+  // the K + 2 slot kernel, four blocks per SM (see step_small_kernel).  Instantiated for K = 10 (the ALAN
+  // shells' maxNeighbors: BASELINE configs 2 and 3) only.
+  if (K == 10 && s->vert_stride <= 4 && s->N <= 32 && std::getenv("ORCA_B200_NO_SLIM_KERNEL") == nullptr)
+    return launch_small_kpo<10, true, POLICY, 2>(s, a, st);
+  return launch_small_kpo<K, KFULL, POLICY, ORCA_MAX_OBST_LINES>(s, a, st);
 }
 
 template <int K, bool KFULL>

@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_
   float2* s_nv = reinterpret_cast<float2*>(s_pool + (ORCA_LP3_SMEM_POOL ? (K + ORCA_MAX_OBST_LINES) * (tpb / 2) : 0));
   int* s_meta = reinterpret_cast<int*>(s_nv + tpb);
   int* s_warp_cnt = s_meta + tpb;
-  unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_warp_cnt + 32);
+  unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_warp_cnt + 8);
   const int T = a.E * a.N;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = j < T;
@@ -527,7 +527,8 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_
     again.env = env;
     again.env_n0 = env * a.N;
     again.self = j;
-    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), again, global_world(a, env), L, slow_mask, c.p, c.v, c.pref), c);
+    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), again, global_world(a, env), L, K + ORCA_MAX_OBST_LINES, slow_mask,
+                                                c.p, c.v, c.pref), c);
   }
   agent_back<POLICY>(a, env, la, g, estep, c);
 }

@@ -328,7 +328,8 @@ ORCA_HD ObstacleWorld global_world(const StepArgs& a, int env) {
 // Front half.  `src` yields the PRE-step state of the other agents (shared-memory tile or
 // uniform-grid cells), `L` is the agent's private line storage, `estep` the env's step counter
 // before this step.  Returns false when the step ends here (neighbors-only parity hook).
-template <int K, bool KFULL, int POLICY, class Src>
+// OL = obstacle-line slots of the agent's line storage (agents that need more take agent_slow_path).
+template <int K, bool KFULL, int POLICY, int OL = ORCA_MAX_OBST_LINES, class Src>
 ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const int estep, const Src& src,
                          const ObstacleWorld& W, const Lines L, const unsigned warp_mask, AgentCarry& c) {
   const float2 p = c.p, v = c.v;
@@ -395,7 +396,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
 
   typename Src::template List<K, KFULL> nk;
   nk.init(a.k, a.nd_sq);
-  src.gather(nk, p, L, K + ORCA_MAX_OBST_LINES, warp_mask);
+  src.gather(nk, p, L, K + OL, warp_mask);
 
   if (a.nbr_idx != nullptr) {
     if (nk.packed_cnt >= 0) nk.unpack_ids();
@@ -419,7 +420,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
 
   // ---------------- ORCA lines ----------------
   int n_obst = 0;
-  if (ocnt > 0) n_obst = obstacle_lines(W, p, v, a.radius, a.inv_tho, od, oid, ocnt, L, &overflow);
+  if (ocnt > 0) n_obst = obstacle_lines<OL>(W, p, v, a.radius, a.inv_tho, od, oid, ocnt, L, &overflow);
   int n = n_obst;
   unsigned collisions = 0;
   {
@@ -439,7 +440,7 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
         w2 = (w2 >> 8) | (w3 << 24);
         w3 >>= 8;
         bool hit;
-        ORCA_DCHECK(n < K + ORCA_MAX_OBST_LINES);
+        ORCA_DCHECK(n < K + OL);
         const float4 ln = agent_line(p, v, src.pos(j), src.vel(j), cr, a.inv_th, a.inv_dt, &hit);
         L.base[n * L.stride] = ln;
         ++n;
@@ -540,7 +541,8 @@ ORCA_HD SlowParams slow_params(const StepArgs& a) {
 }
 template <int K, bool KFULL, class Src>
 ORCA_HD_NOINLINE SlowResult agent_slow_path(const SlowParams a, const Src src, const ObstacleWorld W, const Lines scratch,
-                                            const unsigned mask, const float2 p, const float2 v, const float2 pref) {
+                                            const int scratch_slots, const unsigned mask, const float2 p, const float2 v,
+                                            const float2 pref) {
   bool overflow = false;
   float od[ORCA_SLOW_MAX_OBST];
   int oid[ORCA_SLOW_MAX_OBST];
@@ -553,7 +555,7 @@ ORCA_HD_NOINLINE SlowResult agent_slow_path(const SlowParams a, const Src src, c
   const int n_obst = obstacle_lines<ORCA_SLOW_MAX_OBST>(W, p, v, a.radius, a.inv_tho, od, oid, ocnt, L, &overflow);
   typename Src::template List<K, KFULL> nk;
   nk.init(a.k, a.nd_sq);
-  src.gather(nk, p, scratch, K + ORCA_MAX_OBST_LINES, mask);
+  src.gather(nk, p, scratch, scratch_slots, mask);
   if (nk.packed_cnt >= 0) nk.unpack_ids();
   int n = n_obst;
   unsigned collisions = 0;
@@ -670,7 +672,8 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
   c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];
   if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c)) return;
   if (c.overflow)
-    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), src, global_world(a, env), L, warp_mask, c.p, c.v, c.pref), c);
+    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), src, global_world(a, env), L, K + ORCA_MAX_OBST_LINES, warp_mask,
+                                                c.p, c.v, c.pref), c);
   else
     lp3(warp_mask, c.fail < c.n, L, c.n, c.n_obst, c.fail, a.vmax, c.nv);
   agent_back<POLICY>(a, env, la, g, estep, c);
@@ -690,11 +693,12 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
 #define ORCA_LP3_SMEM_POOL 0
 #endif
 // dynamic shared memory of the step kernels: [pos|vel tile (tile path only)] + lines + LP3 queue
-inline size_t step_smem_bytes(int K, int tpb, bool tile, int world_slots = 0) {
+inline size_t step_smem_bytes(int K, int tpb, bool tile, int world_slots = 0, int obst_lines = ORCA_MAX_OBST_LINES) {
   size_t b = (size_t)world_slots * 64 + 16;  // staged obstacle tables: 4 x 16 B per vertex slot
-  b += (size_t)tpb * ((tile ? 16 : 0) + (size_t)(K + ORCA_MAX_OBST_LINES) * 16 + 8 + 4 + 2) + 32 * 4;
+  // per thread: tile (pos, vel) + lines + LP3 queue (nv 8, meta 4, queue entry 1); per block: 8 warp counters
+  b += (size_t)tpb * ((tile ? 16 : 0) + (size_t)(K + obst_lines) * 16 + 8 + 4 + 1) + 8 * 4;
 #if ORCA_LP3_SMEM_POOL
-  b += (size_t)(tpb / 2) * (K + ORCA_MAX_OBST_LINES) * 16 + 16;  // LP3 projected-line pool
+  b += (size_t)(tpb / 2) * (K + obst_lines) * 16 + 16;  // LP3 projected-line pool
 #endif
   return b;
 }
@@ -714,7 +718,7 @@ inline size_t step_smem_bytes(int K, int tpb, bool tile, int world_slots = 0) {
 #endif
 template <int K>
 __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* s_meta, float2* s_nv,
-                                          unsigned short* s_queue, int* s_warp_cnt, const bool need, const AgentCarry& c, const float vmax,
+                                          unsigned char* s_queue, int* s_warp_cnt, const bool need, const AgentCarry& c, const float vmax,
                                           const bool area_was_borrowed = false) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   // the queue area doubled as the in-block neighbor grid during the front half: nobody may
@@ -748,9 +752,9 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
   {
     const unsigned below = (1u << lane) - 1u;
     if (need)
-      s_queue[offset + __popc(bal & below)] = (unsigned short)tid;
+      s_queue[offset + __popc(bal & below)] = (unsigned char)tid;  // blocks have at most 256 threads
     else
-      s_queue[blockDim.x - 1 - ((warp << 5) - offset + __popc(~bal & below))] = (unsigned short)tid;
+      s_queue[blockDim.x - 1 - ((warp << 5) - offset + __popc(~bal & below))] = (unsigned char)tid;
   }
   __syncthreads();
 #if ORCA_LP3_SMEM_POOL
@@ -799,6 +803,7 @@ __device__ __forceinline__ void block_lp3(float4* s_lines, float4* s_pool, int* 
         for (int q = 0; q < total; ++q) assert((int)s_queue[q] != col);
         for (int q = 0; q < nstored; ++q) assert(q == tid || (int)s_queue[blockDim.x - 1 - q] != col);
         assert(owner >= 0 && owner < (int)blockDim.x && (meta & 0xff) <= K + ORCA_MAX_OBST_LINES);
+        (void)K;
       }
 #endif
       Lines P;
@@ -871,7 +876,7 @@ __device__ __forceinline__ void build_tile_grid(const StepArgs& a, void* area, c
   }
   __syncthreads();
   ORCA_DCHECK(!valid || (start[le * kTileStartStride + ck] + slot < a.N && start[le * kTileStartStride + kTileCells] == a.N));
-  ORCA_DCHECK((char*)(sorted + envs * a.N) - (char*)area <= 14 * (int)blockDim.x + 128);  // the borrowed LP3 queue area
+  ORCA_DCHECK((char*)(sorted + envs * a.N) - (char*)area <= 13 * (int)blockDim.x + 32);  // the borrowed LP3 queue area
   if (valid) sorted[le * a.N + start[le * kTileStartStride + ck] + slot] = (unsigned char)la;
   __syncthreads();
   src.cell_start = start + le * kTileStartStride;
@@ -884,20 +889,26 @@ __device__ __forceinline__ void build_tile_grid(const StepArgs& a, void* area, c
   }
 }
 
-template <int K, bool KFULL, int POLICY>
-__global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) step_small_kernel(const StepArgs a) {
+// OL = obstacle-line slots per agent.  Worlds whose processed obstacle table has at most 4 vertices (no
+// obstacles, or one enclosing wall: BASELINE configs 2 and 3) never give an agent more than 2 obstacle
+// lines (the two edges of a corner), so their kernel keeps K + 2 line slots: 222 instead of 286 bytes of
+// shared memory per thread, which lets FOUR 256-thread blocks share an SM (64 registers) instead of three.
+// Measured (config 2, 214 us at 3 blocks): 2 blocks 272 us, 1 block 480 us -- resident warps are what hides
+// the dependent-instruction latency of the LP chains.
+template <int K, bool KFULL, int POLICY, int OL = ORCA_MAX_OBST_LINES>
+__global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, (OL <= 2 ? 4 : ORCA_STEP_MIN_BLOCKS)) step_small_kernel(const StepArgs a) {
   extern __shared__ float4 smem4[];
   const int tpb = blockDim.x;
-  // [pos | vel] tile: 2 * tpb float2 = tpb float4 ; lines: (K + MAX_OBST_LINES) * tpb float4 ;
-  // LP3 queue: nv (tpb float2), meta (tpb int), queue (tpb u16), warp counters
+  // [pos | vel] tile: 2 * tpb float2 = tpb float4 ; lines: (K + OL) * tpb float4 ;
+  // LP3 queue: nv (tpb float2), meta (tpb int), warp counters, queue (tpb bytes)
   float2* s_pos = reinterpret_cast<float2*>(smem4);
   float2* s_vel = s_pos + tpb;
   float4* s_lines = smem4 + tpb;
-  float4* s_pool = s_lines + (K + ORCA_MAX_OBST_LINES) * tpb;
-  float2* s_nv = reinterpret_cast<float2*>(s_pool + (ORCA_LP3_SMEM_POOL ? (K + ORCA_MAX_OBST_LINES) * (tpb / 2) : 0));
+  float4* s_pool = s_lines + (K + OL) * tpb;
+  float2* s_nv = reinterpret_cast<float2*>(s_pool + (ORCA_LP3_SMEM_POOL ? (K + OL) * (tpb / 2) : 0));
   int* s_meta = reinterpret_cast<int*>(s_nv + tpb);
   int* s_warp_cnt = s_meta + tpb;
-  unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_warp_cnt + 32);
+  unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_warp_cnt + 8);
   // staged obstacle tables (16-byte aligned, after the queue): vert_pd | vert_link | bsp | bsp_seg
   float4* s_world = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(s_queue + tpb) + 15) & ~(uintptr_t)15);
 
@@ -983,7 +994,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
     src.env_vel = s_vel + le * N;
     src.n = N;
     src.self = la;
-    alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, W, L, warp_mask, c);
+    alive = agent_front<K, KFULL, POLICY, OL>(a, env, g, estep, src, W, L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
   block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && !c.overflow && c.fail < c.n, c, a.vmax, tile_grid);
@@ -1002,7 +1013,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ORCA_STEP_MIN_BLOCKS) s
     scan.env_vel = s_vel + le * N;
     scan.n = N;
     scan.self = la;
-    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), scan, global_world(a, env), L, slow_mask, c.p, c.v, c.pref), c);
+    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), scan, global_world(a, env), L, K + OL, slow_mask, c.p, c.v, c.pref), c);
   }
   agent_back<POLICY>(a, env, la, g, estep, c);
 }
