@@ -437,6 +437,18 @@ ORCA_HD float4 agent_line(float2 p, float2 v, float2 po, float2 vo, float cr, fl
 // instead of compare + select + 2 adds.  The sum wraps mod 2^32, i.e. (count * 127 mod 512) sits
 // in bits 23..31; 127 is invertible mod 512 (127 * 383 = 95 * 512 + 1), which recovers any
 // count below 512.
+// bit pattern of 1.0f when x < y, else 0; and the number of such patterns summed into a word
+ORCA_HD unsigned lt_as_one_bits(float x, float y) {
+#if defined(__CUDA_ARCH__)
+  float one_or_zero;
+  asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(one_or_zero) : "f"(x), "f"(y));
+  return __float_as_uint(one_or_zero);
+#else
+  return (x < y) ? 0x3f800000u : 0u;
+#endif
+}
+ORCA_HD int one_bits_count(unsigned sum) { return (int)(((sum >> 23) * 383u) & 511u); }  // counts below 512
+
 template <int M>
 ORCA_HD void rank_count(const float* d, int* r) {
 #if defined(__CUDA_ARCH__)

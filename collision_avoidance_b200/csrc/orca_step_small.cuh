@@ -159,6 +159,103 @@ struct TileSource {
     }
     nk.set_sorted_ids(*reinterpret_cast<const uint4*>(scratch.base), cnt);
   }
+  // Worlds of 17..32 agents: the same ranks without 32 keys + 32 counters live in registers at once
+  // (gather_ranked<32> peaks above 64 registers, which the 4-blocks-per-SM kernel does not have).
+  // Keys 0..15 (A) stay in registers, keys 16..31 (B) go to the agent's (still unused) line column.
+  //   rank(a) = rank within A + #{b : d_b <  d_a}      (a tie keeps the lower index, an A key, in front)
+  //   rank(b) = rank within B + #{a : !(d_b < d_a)}
+  // 120 + 256 + 120 pair tests -- as many as rank_count<32> -- with the 256 cross tests in a rolled loop.
+  // Column layout: slot 0 = the sorted id bytes (output), slots 1-4 = d_B, slots 5-8 = #A keys in front of b.
+  template <class NK>
+  ORCA_HD void gather_ranked32(NK& nk, float2 p, const Lines& scratch) const {
+    float dA[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 q = env_pos[j < n ? j : 0];
+      const float pad = (j < n && j != self) ? 0.f : INFINITY;
+      dA[j] = abs_sq(sub(p, q)) + pad;
+    }
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      float t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = 16 + 4 * g4 + u;
+        const float2 q = env_pos[j < n ? j : 0];
+        const float pad = (j < n && j != self) ? 0.f : INFINITY;
+        t[u] = abs_sq(sub(p, q)) + pad;
+      }
+      float4 w;
+      w.x = t[0];
+      w.y = t[1];
+      w.z = t[2];
+      w.w = t[3];
+      scratch.base[(1 + g4) * scratch.stride] = w;
+    }
+    int rA[16];
+    rank_count<16>(dA, rA);
+    // counts as sums of the BIT PATTERN of 1.0f (see rank_count): one FSET per pair, integer adds
+    unsigned crossA[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) crossA[a] = 0u;
+#pragma unroll 1
+    for (int g4 = 0; g4 < 4; ++g4) {
+      const float4 w = scratch.base[(1 + g4) * scratch.stride];
+      const float b[4] = {w.x, w.y, w.z, w.w};
+      unsigned sum[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int a = 0; a < 16; ++a) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned f = lt_as_one_bits(b[u], dA[a]);
+          crossA[a] += f;
+          sum[u] += f;
+        }
+      }
+      float4 o;  // #A keys in front of b = 16 - #{a : d_b < d_a}
+      o.x = bits_to_float(16 - one_bits_count(sum[0]));
+      o.y = bits_to_float(16 - one_bits_count(sum[1]));
+      o.z = bits_to_float(16 - one_bits_count(sum[2]));
+      o.w = bits_to_float(16 - one_bits_count(sum[3]));
+      scratch.base[(5 + g4) * scratch.stride] = o;
+    }
+    float dB[16];
+    int crossB[16];
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      const float4 w = scratch.base[(1 + g4) * scratch.stride];
+      const float4 o = scratch.base[(5 + g4) * scratch.stride];
+      dB[4 * g4] = w.x;
+      dB[4 * g4 + 1] = w.y;
+      dB[4 * g4 + 2] = w.z;
+      dB[4 * g4 + 3] = w.w;
+      crossB[4 * g4] = float_to_bits(o.x);
+      crossB[4 * g4 + 1] = float_to_bits(o.y);
+      crossB[4 * g4 + 2] = float_to_bits(o.z);
+      crossB[4 * g4 + 3] = float_to_bits(o.w);
+    }
+    unsigned char* slot = reinterpret_cast<unsigned char*>(scratch.base);
+    int cnt = 0;
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      const int r = rA[a] + one_bits_count(crossA[a]);
+      const bool in = dA[a] < nk.range_sq && r < nk.k;
+      cnt += in ? 1 : 0;
+      ORCA_DCHECK(!in || (r >= 0 && r < 16));
+      if (in) slot[r] = (unsigned char)a;
+    }
+    int rB[16];
+    rank_count<16>(dB, rB);
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      const int r = rB[b] + crossB[b];
+      const bool in = dB[b] < nk.range_sq && r < nk.k;
+      cnt += in ? 1 : 0;
+      ORCA_DCHECK(!in || (r >= 0 && r < 16));
+      if (in) slot[r] = (unsigned char)(16 + b);
+    }
+    nk.set_sorted_ids(*reinterpret_cast<const uint4*>(scratch.base), cnt);
+  }
   template <class NK>
   ORCA_HD void gather(NK& nk, float2 p, const Lines& scratch, int scratch_slots, unsigned mask) const {
 #ifndef ORCA_NO_RANKED16  // A/B switch: -DORCA_NO_RANKED16 builds the insertion path for small worlds too
@@ -167,7 +264,11 @@ struct TileSource {
       return;
     }
     if (n <= 32) {
+#ifdef ORCA_RANKED32_FLAT  // A/B switch: all 32 keys in registers
       gather_ranked<32>(nk, p, scratch);
+#else
+      gather_ranked32(nk, p, scratch);
+#endif
       return;
     }
 #endif
