@@ -426,6 +426,36 @@ ORCA_HD ObstacleWorld global_world(const StepArgs& a, int env) {
   return W;
 }
 
+// ALAN action selection (ALAN_true.py:580-586): p = softmax(w / temp); the action is the first one
+// whose running sum of UNNORMALISED weights exceeds u * total -- np.random.choice's inverse-CDF draw.
+template <int MAXA>
+ORCA_HD int alan_select(const float* wrow, const int nA, const float inv_temp, const float u) {
+  float w_act[MAXA];
+  float total = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXA; ++i) {
+    if (i < nA) {
+      w_act[i] = expf(wrow[i] * inv_temp);
+      total += w_act[i];
+    }
+  }
+  const float target = u * total;
+  float run = 0.f;
+  int act = nA - 1;
+  bool found = false;
+#pragma unroll
+  for (int i = 0; i < MAXA; ++i) {
+    if (i < nA) {
+      run += w_act[i];
+      if (!found && run > target) {
+        act = i;
+        found = true;
+      }
+    }
+  }
+  return act;
+}
+
 // Front half.  `src` yields the PRE-step state of the other agents (shared-memory tile or
 // uniform-grid cells), `L` is the agent's private line storage, `estep` the env's step counter
 // before this step.  Returns false when the step ends here (neighbors-only parity hook).
@@ -439,7 +469,6 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
   float2 gdir = v2(0.f, 0.f);
   float2 pref;
   int act = 0;
-  float w_act[POLICY == POLICY_ALAN ? ORCA_MAX_ACTIONS : 1];
   if (POLICY == POLICY_EXTERNAL) {
     pref = c.aim;
   } else {
@@ -455,31 +484,12 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
       const float* wrow = a.alan_w + (size_t)g * a.A;
       const int nA = (a.alan_A_env != nullptr) ? a.alan_A_env[env] : a.A;  // this env's action count
       const float2* table = a.alan_actions + (size_t)env * a.alan_env_stride;
-      float total = 0.f;
-#pragma unroll
-      for (int i = 0; i < ORCA_MAX_ACTIONS; ++i) {
-        if (i < nA) {
-          w_act[i] = expf(wrow[i] * a.alan_inv_temp);
-          total += w_act[i];
-        }
-      }
       const float u = (a.alan_uniform_in != nullptr)
                           ? a.alan_uniform_in[g]
                           : philox_uniform(a.seed, (uint32_t)g, (uint32_t)estep);
-      const float target = u * total;
-      float run = 0.f;
-      act = nA - 1;
-      bool found = false;
-#pragma unroll
-      for (int i = 0; i < ORCA_MAX_ACTIONS; ++i) {
-        if (i < nA) {
-          run += w_act[i];
-          if (!found && run > target) {
-            act = i;
-            found = true;
-          }
-        }
-      }
+      // the loops are unrolled to a compile-time bound (the weights stay in registers); the common
+      // sets (the reference's default 8 actions and every .act table but two) take the short one
+      act = (a.A <= 8) ? alan_select<8>(wrow, nA, a.alan_inv_temp, u) : alan_select<ORCA_MAX_ACTIONS>(wrow, nA, a.alan_inv_temp, u);
       pref = rotate(gdir, table[act]);
       if (a.alan_action_out != nullptr) a.alan_action_out[g] = (uint8_t)act;
     }
