@@ -29,6 +29,7 @@
 
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -459,8 +460,10 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float2* __restr
 #endif
 // G6: the fused step over the cell-sorted order.  Thread j handles the agent in sorted slot j, so a
 // warp's agents share cells (coherent candidate loops, cache-friendly reads).
-template <int K, bool KFULL, int POLICY>
-__global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_kernel(const StepArgs a, const float4* __restrict__ spv,
+// OL: obstacle-line slots per agent, as in step_small_kernel: the K + 2 variant (worlds of at most 4
+// obstacle vertices) fits 1024 instead of 768 threads per SM.
+template <int K, bool KFULL, int POLICY, int OL = ORCA_MAX_OBST_LINES>
+__global__ void __launch_bounds__(ORCA_GRID_TPB, (OL <= 2 ? 1024 : 768) / ORCA_GRID_TPB) step_grid_kernel(const StepArgs a, const float4* __restrict__ spv,
                                                            const int* __restrict__ sidx,
                                                            const int* __restrict__ cell_start,
                                                            const GridParams* __restrict__ gpp,
@@ -468,8 +471,8 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_
   extern __shared__ float4 smem4[];
   const int tpb = blockDim.x;
   float4* s_lines = smem4;
-  float4* s_pool = s_lines + (K + ORCA_MAX_OBST_LINES) * tpb;
-  float2* s_nv = reinterpret_cast<float2*>(s_pool + (ORCA_LP3_SMEM_POOL ? (K + ORCA_MAX_OBST_LINES) * (tpb / 2) : 0));
+  float4* s_pool = s_lines + (K + OL) * tpb;
+  float2* s_nv = reinterpret_cast<float2*>(s_pool + (ORCA_LP3_SMEM_POOL ? (K + OL) * (tpb / 2) : 0));
   int* s_meta = reinterpret_cast<int*>(s_nv + tpb);
   int* s_warp_cnt = s_meta + tpb;
   unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_warp_cnt + 8);
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_
     c.p = v2(pv.x, pv.y);
     c.v = v2(pv.z, pv.w);
     if (!a.neighbors_only) c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];
-    alive = agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c);
+    alive = agent_front<K, KFULL, POLICY, OL>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
   block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && !c.overflow && c.fail < c.n, c, a.vmax);
@@ -527,8 +530,7 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, 768 / ORCA_GRID_TPB) step_grid_
     again.env = env;
     again.env_n0 = env * a.N;
     again.self = j;
-    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), again, global_world(a, env), L, K + ORCA_MAX_OBST_LINES, slow_mask,
-                                                c.p, c.v, c.pref), c);
+    apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), again, global_world(a, env), L, K + OL, slow_mask, c.p, c.v, c.pref), c);
   }
   agent_back<POLICY>(a, env, la, g, estep, c);
 }
@@ -581,8 +583,8 @@ inline int grid_ensure(GridScratch& G, const StepArgs& a, cudaStream_t st, std::
 
 constexpr int kGridLaunchesPerStep = 5;  // G1 bounds, G2 count, G3 scan, G4 scatter, G5 step
 
-template <int K, bool KFULL, int POLICY>
-int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* launches, std::string* err) {
+template <int K, bool KFULL, int POLICY, int OL>
+int launch_grid_kpo(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* launches, std::string* err) {
   const int T = a.E * a.N;
   const int rc = grid_ensure(G, a, st, err);
   if (rc != 0) return rc;
@@ -600,14 +602,15 @@ int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* 
   StepArgs args = a;
   // the step kernel only READS the step counters in this path, from the copy G2 made
   const int stpb = ORCA_GRID_TPB;
-  const size_t smem = step_smem_bytes(K, stpb, false);
-  auto kern = step_grid_kernel<K, KFULL, POLICY>;
+  const size_t smem = step_smem_bytes(K, stpb, false, 0, OL);
+  auto kern = step_grid_kernel<K, KFULL, POLICY, OL>;
   int dev = 0;
   ORCA_GRID_TRY(cudaGetDevice(&dev));
   // function attributes are per device; setting one is idempotent, so a racing second thread is harmless
   static std::atomic<bool> attr_set[kMaxDevices];
   if (dev >= kMaxDevices || !attr_set[dev].load(std::memory_order_acquire)) {
     ORCA_GRID_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ORCA_GRID_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     if (dev < kMaxDevices) attr_set[dev].store(true, std::memory_order_release);
   }
   args.grid_path = 1;
@@ -615,6 +618,14 @@ int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* 
   ORCA_GRID_TRY(cudaGetLastError());
   *launches += kGridLaunchesPerStep;
   return 0;
+}
+
+template <int K, bool KFULL, int POLICY>
+int launch_grid_kp(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t* launches, std::string* err) {
+  // at most 4 obstacle vertices (none, or one wall): an agent never has more than 2 obstacle lines
+  if (K == 10 && a.world_verts <= 4 && a.vert_stride == 0 && std::getenv("ORCA_B200_NO_SLIM_KERNEL") == nullptr)
+    return launch_grid_kpo<10, true, POLICY, 2>(G, a, st, launches, err);
+  return launch_grid_kpo<K, KFULL, POLICY, ORCA_MAX_OBST_LINES>(G, a, st, launches, err);
 }
 
 template <int K, bool KFULL>
