@@ -216,6 +216,9 @@ int launch_small_kp(OrcaSim* s, const orca::StepArgs& a, cudaStream_t st) {
   // a world of at most 4 processed vertices (none, or one wall) gives an agent at most 2 obstacle lines:
   // the K + 2 slot kernel, four blocks per SM (see step_small_kernel).  Instantiated for K = 10 (the ALAN
   // shells' maxNeighbors: BASELINE configs 2 and 3) only.
+  // (worlds of more than 32 agents search through the candidate buffer, which lives in the line slots:
+  // with 12 instead of 16 of them the smaller buffer costs more than the fourth block gains -- measured
+  // 509 vs 501 us for 50-agent crowds, 497 vs 492 us for 256-agent crowds)
   if (K == 10 && s->vert_stride <= 4 && s->N <= 32 && std::getenv("ORCA_B200_NO_SLIM_KERNEL") == nullptr)
     return launch_small_kpo<10, true, POLICY, 2>(s, a, st);
   return launch_small_kpo<K, KFULL, POLICY, ORCA_MAX_OBST_LINES>(s, a, st);
