@@ -79,7 +79,8 @@ enum {
   ORCA_STAT_FINISHED = 1,     /* u64: agents that reached their goal */
   ORCA_STAT_COLLISIONS = 2,   /* u64: (agent, neighbor) pairs with distSq <= (2r)^2 (RVO2's collision branch) */
   ORCA_STAT_LP3_CALLS = 3,    /* u64: agents whose LP2 was infeasible */
-  ORCA_STAT_OVERFLOW = 4,     /* u64: agents that exceeded the obstacle-neighbor / line capacity */
+  ORCA_STAT_OVERFLOW = 4,     /* u64: agent-steps that exceeded even the uncapped path's capacity (64 obstacle edges /
+                               * lines per agent): a constraint was dropped; impossible for worlds of <= 64 vertices */
   ORCA_STAT_SUM_ARRIVAL = 5,  /* f64: sum of arrival times  (TTime, ALAN_true.py:125-131) */
   ORCA_STAT_SUM_ARRIVAL2 = 6, /* f64: sum of squared arrival times */
   ORCA_STAT_SUM_REWARD = 7,   /* f64: sum of the per-agent rewards (RL and ALAN policies) */
@@ -142,8 +143,10 @@ typedef struct OrcaEnvStepArgs {
   uint64_t* stats_dev; /* [ORCA_STAT_COUNT] accumulated, optional */
 } OrcaEnvStepArgs;
 
-#define ORCA_MAX_OBST_NEIGHBORS 16 /* per agent; farther edges set ORCA_STAT_OVERFLOW */
-#define ORCA_MAX_OBST_LINES 6      /* obstacle ORCA lines kept per agent */
+#define ORCA_MAX_OBST_NEIGHBORS 16 /* width of the obstacle neighbor-list OUTPUT (the 16 nearest edges) */
+#define ORCA_MAX_OBST_LINES 6      /* obstacle ORCA lines of the fast path; agents with more (or with more than 16
+                                    * obstacle neighbors) are redone by the uncapped path (64 of each) -- RVO2 has
+                                    * no cap (insertObstacleNeighbor), and neither has the step */
 #define ORCA_MAX_ACTIONS 16
 
 /* ---- lifecycle ---------------------------------------------------------------- */
