@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(kBoundsThreads) grid_bounds_kernel(const float
 __global__ void __launch_bounds__(256) grid_count_kernel(const float2* __restrict__ pos, int T, int N,
                                                          const GridParams* __restrict__ gpp, int* cell_count,
                                                          int* __restrict__ key, int* __restrict__ slot, int* env_step,
+                                                         const int* __restrict__ env_done_cnt,
                                                          int* __restrict__ env_step_snap, int E, int bump) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (env_step != nullptr && i < E) {
@@ -328,6 +329,9 @@ __global__ void __launch_bounds__(256) grid_count_kernel(const float2* __restric
     env_step_snap[i] = s0;
     if (bump) env_step[i] = s0 + 1;
   }
+  // [E, 2E): how many agents of the env had arrived when this step began (the step kernel's blocks of one
+  // env must agree on whether the episode was still running; its own arrivals are counted as it goes)
+  if (i < E) env_step_snap[E + i] = (env_done_cnt != nullptr) ? env_done_cnt[i] : 0;
   if (i >= T) return;
   const GridParams gp = *gpp;
   const float2 p = pos[i];
@@ -487,13 +491,14 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, (OL <= 2 ? 1024 : 768) / ORCA_G
   c.aim = v2(0.f, 0.f);
   c.n = c.n_obst = c.fail = 0;
   int g = 0, env = 0, la = 0, estep = 0;
-  bool alive = valid;
+  bool alive = valid, env_live = true;
   c.overflow = false;
   if (valid) {
     g = sidx[j];
     env = g / a.N;
     la = g - env * a.N;
     estep = (a.env_step != nullptr) ? env_step_snap[env] : 0;
+    env_live = env_step_snap[a.E + env] < a.N;
     GridSource src;
     src.spv = spv;
     src.orig = sidx;
@@ -532,7 +537,7 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, (OL <= 2 ? 1024 : 768) / ORCA_G
     again.self = j;
     apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), again, global_world(a, env), L, K + OL, slow_mask, c.p, c.v, c.pref), c);
   }
-  agent_back<POLICY>(a, env, la, g, estep, c);
+  agent_back<POLICY>(a, env, la, g, estep, c, env_live);
 }
 
 #define ORCA_GRID_TRY(expr)                                                         \
@@ -575,7 +580,7 @@ inline int grid_ensure(GridScratch& G, const StepArgs& a, cudaStream_t st, std::
   ORCA_GRID_TRY(cudaMalloc(&G.cell_count, ((size_t)G.cap_cells + 1) * sizeof(int)));
   ORCA_GRID_TRY(cudaMalloc(&G.cell_start, ((size_t)G.cap_cells + 1) * sizeof(int)));
   ORCA_GRID_TRY(cudaMalloc(&G.tile_state, tiles * sizeof(unsigned long long)));
-  ORCA_GRID_TRY(cudaMalloc(&G.env_step_snap, (size_t)a.E * sizeof(int)));
+  ORCA_GRID_TRY(cudaMalloc(&G.env_step_snap, 2 * (size_t)a.E * sizeof(int)));
   ORCA_GRID_TRY(cudaMemsetAsync(G.cell_count, 0, ((size_t)G.cap_cells + 1) * sizeof(int), st));
   ORCA_GRID_TRY(cudaMemsetAsync(G.tile_state, 0, tiles * sizeof(unsigned long long), st));
   return 0;
@@ -592,7 +597,7 @@ int launch_grid_kpo(GridScratch& G, const StepArgs& a, cudaStream_t st, int64_t*
   const int nb_agents = (T + tpb - 1) / tpb;
   grid_bounds_kernel<<<G.sm_count * 2, kBoundsThreads, 0, st>>>(a.pos, T, G.counters, sqrtf(a.nd_sq), a.E, G.cap_cells, G.params);
   grid_count_kernel<<<nb_agents, tpb, 0, st>>>(a.pos, T, a.N, G.params, G.cell_count, G.key, G.slot, a.env_step,
-                                               G.env_step_snap, a.E, a.neighbors_only ? 0 : 1);
+                                               a.env_done_cnt, G.env_step_snap, a.E, a.neighbors_only ? 0 : 1);
   const int scan_blocks = (G.cap_cells + kScanTile - 1) / kScanTile;
   G.epoch = (G.epoch + 1u) & 0x3fffffffu;
   if (G.epoch == 0u) G.epoch = 1u;  // 0 is the state of freshly cleared words

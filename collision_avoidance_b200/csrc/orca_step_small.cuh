@@ -703,11 +703,14 @@ ORCA_HD void apply_slow_result(const SlowResult& r, AgentCarry& c) {
 }
 
 // Back half: Agent::update + reward + bandit update + done test, with c.nv final.
+// `live`: the agent's world had not finished its episode when this step began.  In a batch, worlds that
+// finish early keep being stepped until the slowest one is done (run_sim), but their idle steps must not
+// leak into the episode statistics (the reference's run_sim stops stepping a finished world, ALAN_true.py:121).
 template <int POLICY>
 ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const int g, const int estep,
-                        const AgentCarry& c) {
-  stat_add_u64_warp(a.stats, STAT_AGENT_STEPS, 1u);
-  stat_add_u64_warp(a.stats, STAT_LP3_CALLS, c.fail < c.n ? 1u : 0u);
+                        const AgentCarry& c, const bool live = true) {
+  stat_add_u64_warp(a.stats, STAT_AGENT_STEPS, live ? 1u : 0u);
+  stat_add_u64_warp(a.stats, STAT_LP3_CALLS, (live && c.fail < c.n) ? 1u : 0u);
 
   // ---------------- integrate (Agent::update) ----------------
   const float2 v = c.nv;
@@ -727,7 +730,7 @@ ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const in
     else
       R = a.alan_gamma * r_goal + (1.f - a.alan_gamma) * r_polite;
     if (a.reward != nullptr) a.reward[g] = R;
-    stat_add_f64_warp(a.stats, STAT_SUM_REWARD, R);
+    stat_add_f64_warp(a.stats, STAT_SUM_REWARD, live ? R : 0.f);
     if (POLICY == POLICY_ALAN) {
       float* wrow = a.alan_w + (size_t)g * a.A;
       // every per-action timer advances in lock step, so the 2 s window expires for all of
@@ -771,7 +774,7 @@ ORCA_HD void agent_back(const StepArgs& a, const int env, const int la, const in
     }
   }
   if (a.env_step != nullptr && la == 0 && !a.grid_path) a.env_step[env] = estep + 1;
-  stat_add_u64_warp(a.stats, STAT_COLLISIONS, c.collisions);
+  stat_add_u64_warp(a.stats, STAT_COLLISIONS, live ? c.collisions : 0u);
   stat_add_u64_warp(a.stats, STAT_OVERFLOW, c.overflow ? 1u : 0u);
 }
 
@@ -1041,6 +1044,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, (OL <= 2 ? 4 : ORCA_STE
   c.nv = v2(0.f, 0.f);
   c.n = c.n_obst = c.fail = 0;
   int estep = 0;
+  bool env_live = true;
   c.aim = v2(0.f, 0.f);
   if (valid) {
     // consumed after the barrier (with the in-block grid the thread changes agents below and loads it then)
@@ -1050,6 +1054,8 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, (OL <= 2 ? 4 : ORCA_STE
     s_pos[tid] = c.p;
     s_vel[tid] = c.v;
     if (a.env_step != nullptr) estep = a.env_step[env];
+    // read before the first barrier: nobody of this env (= this block) has counted an arrival of this step yet
+    if (a.env_done_cnt != nullptr) env_live = a.env_done_cnt[env] < N;
   }
   // The BSP walk is a chain of dependent node loads done by every agent every step: from global
   // memory each hop is an L2 round trip.  The tables are tiny (64 B per vertex), so the block
@@ -1128,7 +1134,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, (OL <= 2 ? 4 : ORCA_STE
     scan.self = la;
     apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), scan, global_world(a, env), L, K + OL, slow_mask, c.p, c.v, c.pref), c);
   }
-  agent_back<POLICY>(a, env, la, g, estep, c);
+  agent_back<POLICY>(a, env, la, g, estep, c, env_live);
 }
 
 #endif  // __CUDACC__

@@ -180,8 +180,10 @@ int orca_step(OrcaSim* sim, float* pos_dev, float* vel_dev, const float* pref_de
 /* Fused environment step: policy + doStep + reward + done test + bandit update. */
 int orca_env_step(OrcaSim* sim, const OrcaEnvStepArgs* args, void* stream);
 /* `steps` fused environment steps back to back on `stream` without returning to the host in
- * between (run_sim's inner loop, ALAN_true.py:113-121): removes the per-step host overhead that
- * dominates small batches.  Same arguments as orca_env_step. */
+ * between (run_sim's inner loop, ALAN_true.py:113-121): the launches are issued from C, which removes the
+ * per-step Python / ctypes cost (the launches themselves are asynchronous either way).  Same arguments as
+ * orca_env_step.  Worlds whose env_done_cnt had reached agents_per_env when a step began keep being
+ * stepped, but no longer count into stats_dev (agent steps, collisions, LP3 calls, reward sum). */
 int orca_env_step_many(OrcaSim* sim, const OrcaEnvStepArgs* args, int steps, void* stream);
 /* Parity hook: neighbor search only.  nbr_distsq_dev optional. */
 int orca_neighbors(OrcaSim* sim, const float* pos_dev, int32_t* nbr_idx_dev, float* nbr_distsq_dev,

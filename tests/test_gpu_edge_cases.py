@@ -298,3 +298,27 @@ def test_host_entry_point_reduced_traffic_variants(monkeypatch, mode):
     full.step_host(pf, vf, gf, policy=_lib.POLICY_GOAL, upload_state=False)
     lean.step_host(pl, vl, gl, policy=_lib.POLICY_GOAL, upload_state=False)
     assert torch.equal(pf, pl) and torch.equal(vf, vl)
+
+
+@pytest.mark.parametrize("N", [8, 300])
+def test_finished_worlds_stop_counting_statistics(N):
+    """Worlds that finish early keep being stepped (run_sim polls rarely), but their idle steps do not
+    count into the episode statistics -- tile path and uniform-grid path."""
+    import torch
+    from collision_avoidance_b200 import _lib, scenarios
+    scn = scenarios.crowd(2, N, seed=3)
+    scn.goal[0] = scn.pos[0]            # world 0: everybody already stands on the goal -> done after step 1
+    scn.goal2[0] = scn.pos[0]
+    sim = _mk(scn)
+    E = 2
+    st = dict(goal=torch.from_numpy(scn.goal).cuda(), goal2=torch.from_numpy(scn.goal2).cuda(),
+              agent_done=torch.zeros(E, N, dtype=torch.uint8, device="cuda"), arrival_time=torch.zeros(E, N, device="cuda"),
+              env_step=torch.zeros(E, dtype=torch.int32, device="cuda"), env_done_cnt=torch.zeros(E, dtype=torch.int32, device="cuda"))
+    steps = 20
+    for _ in range(steps):
+        sim.env_step(policy=_lib.POLICY_GOAL, done_mode=_lib.DONE_GOAL_RADIUS, **st)
+    assert int(st["env_done_cnt"][0]) == N and int(st["env_done_cnt"][1]) < N
+    assert st["env_step"].tolist() == [steps, steps]                 # both worlds were stepped ...
+    s = sim.read_stats()
+    assert s["agent_steps"] == N + steps * N                         # ... world 0 counted for its one live step only
+    assert s["finished"] >= N
