@@ -108,6 +108,7 @@ struct OrcaSim {
   HostGraphKey tune_key{};
   int tune_calls = 0;
   double tune_ms[2] = {0.0, 0.0};  // [direct, staged]
+  float* d_nbr_hint = nullptr;  // [E*N] per-agent starting threshold of the neighbor search (see agent_front)
   // uniform-grid scratch (large worlds)
   orca::GridScratch grid;
   int64_t launches = 0;
@@ -240,7 +241,14 @@ int launch_small_k(OrcaSim* s, const orca::StepArgs& a, int policy, cudaStream_t
   }
 }
 
-int launch_step(OrcaSim* s, const orca::StepArgs& a, int policy, cudaStream_t st) {
+int launch_step(OrcaSim* s, const orca::StepArgs& a0, int policy, cudaStream_t st) {
+  orca::StepArgs a = a0;
+  // searches that run on a shrinking threshold (worlds of more than 32 agents) start from last step's
+  // k-th neighbor distance; the parity hook orca_neighbors stays stateless
+  if (s->d_nbr_hint != nullptr && !a.neighbors_only && std::getenv("ORCA_B200_NO_NBR_HINT") == nullptr) {
+    a.nbr_hint = s->d_nbr_hint;  // allocated by orca_create (never inside a launch: the host path captures graphs)
+    a.hint_slack = 2.5f * s->p.max_speed * s->p.time_step + 1e-4f;
+  }
   if (s->N >= s->grid_min_agents) {
     return orca::launch_grid_step(s->grid, a, policy, st, &s->launches, &g_last_error);
   }
@@ -295,6 +303,15 @@ int orca_create(const OrcaParams* params, int device, int num_envs, int agents_p
     const int v = std::atoi(e);
     if (v >= 1 && v <= 257) s->grid_min_agents = v;
   }
+  if (s->N > 32) {  // starting thresholds of the threshold searches (agent_front); 0x7f7f7f7f = 3.4e38: no hint yet
+    const size_t n = (size_t)s->E * s->N;
+    if (cudaMalloc(&s->d_nbr_hint, n * sizeof(float)) != cudaSuccess || cudaMemset(s->d_nbr_hint, 0x7f, n * sizeof(float)) != cudaSuccess) {
+      const int rc = fail(ORCA_ERR_CUDA, "allocating the neighbor-search scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      cudaFree(s->d_nbr_hint);
+      delete s;
+      return rc;
+    }
+  }
   *out = s;
   return ORCA_OK;
 }
@@ -306,6 +323,7 @@ int orca_destroy(OrcaSim* s) {
   cudaFree(s->d_pos);
   cudaFree(s->d_vel);
   cudaFree(s->d_aux);
+  cudaFree(s->d_nbr_hint);
   if (s->host_graph_exec) cudaGraphExecDestroy(s->host_graph_exec);
   for (int c = 0; c < kHostChunksMax; ++c) {
     if (s->host_streams[c]) cudaStreamDestroy(s->host_streams[c]);

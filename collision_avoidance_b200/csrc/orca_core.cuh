@@ -552,6 +552,9 @@ struct NearestK {
     }
   }
   ORCA_HD void finish() {}
+  // the list holds k neighbors / squared distance of the k-th (KFULL lists only)
+  ORCA_HD bool full() const { return id[K - 1] >= 0; }
+  ORCA_HD float kth_dist_sq() const { return d[K - 1]; }
   // Candidates arrive in arbitrary order (uniform-grid cells): order by (distance, rank) where
   // `precedes(a, b)` says whether entry a goes before entry b at equal distance (b may be -1 = empty
   // slot, which nothing precedes).  Gives the same list as ascending-id visiting.
@@ -645,6 +648,9 @@ struct NearestKeys {
 #pragma unroll
     for (int s = 0; s < K; ++s) id[s] = (int)(unsigned)(key[s] & 0xffffffffull) - 1;
   }
+  // the list holds k neighbors / squared distance of the k-th (KFULL lists only; after finish())
+  ORCA_HD bool full() const { return id[K - 1] >= 0; }
+  ORCA_HD float kth_dist_sq() const { return bits_to_float((int)(unsigned)(key[K - 1] >> 32)); }
   // ids below 256 (the tile kernel's in-env ids): also hand the list over as bytes, like
   // set_sorted_ids does, so that its consumers can walk it with a rolled loop.  The valid entries
   // are a prefix of the list (empty slots carry the largest key).

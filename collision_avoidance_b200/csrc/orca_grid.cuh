@@ -119,6 +119,11 @@ struct GridSource {
     return c >= n ? n - 1 : c;
   }
 
+  ORCA_HD bool threshold_search() const { return true; }
+  float full_range_sq = 0.f;  // the neighbor range (squared), for the second pass
+  // The list arrives initialised with its STARTING threshold (agent_front): the neighbor range or last
+  // step's tighter bound.  Lanes whose list did not fill up from a tighter start search again from the
+  // full range in a second pass over the same rows.
   template <class NK>
   ORCA_HD void gather(NK& nk, float2 p, const Lines& scratch, int scratch_slots, unsigned mask) const {
     // cell coordinates as floats: same expression as cell_coord, so "agent q is in cell c" means
@@ -144,12 +149,21 @@ struct GridSource {
     // between the agent and the row / column: an agent binned there cannot be nearer than the gap.
     // Border cells also hold the agents clamped into them from outside the box, which are farther
     // still; the agent's OWN row and column are never pruned (it may itself be a clamped one).
+    constexpr int kRows = 2 * kGridReach + 1;
+    bool enabled = true;
 #pragma unroll 1
-    for (int r = 0; r < 2 * kGridReach + 1; ++r) {
+    for (int rr = 0; rr < 2 * kRows; ++rr) {
+      if (rr == kRows) {  // second pass?
+        buf.drain(mask, insert);
+        enabled = nk.range_sq < full_range_sq && !nk.full();
+        if (!ORCA_ANY(mask, enabled)) break;
+        if (enabled) nk.init(nk.k, full_range_sq);
+      }
+      const int r = rr < kRows ? rr : rr - kRows;
       const int dy = (r & 1) ? -((r + 1) >> 1) : (r >> 1);  // 0, -1, +1, -2, +2
       const int yy = cy + dy;
       int q = 0, last = 0;
-      if (yy >= 0 && yy < gp.H) {
+      if (enabled && yy >= 0 && yy < gp.H) {
         int x0 = cx - kGridReach > 0 ? cx - kGridReach : 0;
         int x1 = cx + kGridReach < gp.W ? cx + kGridReach : gp.W - 1;
         bool visit = true;
@@ -501,6 +515,7 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, (OL <= 2 ? 1024 : 768) / ORCA_G
     env_live = env_step_snap[a.E + env] < a.N;
     GridSource src;
     src.spv = spv;
+    src.full_range_sq = a.nd_sq;
     src.orig = sidx;
     src.cell_start = cell_start;
     src.gp = *gpp;

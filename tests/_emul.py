@@ -34,6 +34,7 @@ class StepArgs(ctypes.Structure):
         ("vert_pd", c_p), ("vert_link", c_p), ("bsp", c_p), ("bsp_seg", c_p), ("env_nodes", c_p),
         ("shared_nodes", c_i), ("vert_stride", c_i), ("world_slots", c_i), ("world_verts", c_i), ("neighbors_only", c_i), ("grid_path", c_i),
         ("pos_mirror", c_p), ("vel_mirror", c_p), ("tile_grid_inv_cell", c_f),
+        ("nbr_hint", c_p), ("hint_slack", c_f),
     ]
 
 
@@ -105,7 +106,8 @@ class World:
 def emul_step(params, pos, vel, *, policy=0, pref=None, goal=None, goal2=None, world=None, action_theta=None,
               rl_scale=0.3, done_x=2.0, alan_w=None, alan_actions=None, alan_uniform=None, alan_window=121,
               alan_gamma=0.6, alan_temp=0.2, seed=0, done_mode=0, agent_done=None, arrival=None, env_step=None,
-              env_done_cnt=None, want_neighbors=False, neighbors_only=False, stats=None, grid=False, tile_grid=None):
+              env_done_cnt=None, want_neighbors=False, neighbors_only=False, stats=None, grid=False, tile_grid=None,
+              nbr_hint=None):
     """Run one fused step on host arrays, in place.  pos/vel: float32 [E, N, 2].
     Returns dict with optional outputs (reward, action, nbr_idx, nbr_cnt, ...)."""
     E, N = pos.shape[0], pos.shape[1]
@@ -155,6 +157,10 @@ def emul_step(params, pos, vel, *, policy=0, pref=None, goal=None, goal2=None, w
         a.nbr_idx, a.nbr_dsq, a.nbr_cnt = _ptr(out["nbr_idx"]), _ptr(out["nbr_dsq"]), _ptr(out["nbr_cnt"])
         a.onbr_idx, a.onbr_cnt = _ptr(out["onbr_idx"]), _ptr(out["onbr_cnt"])
     a.stats = _ptr(stats)
+    if nbr_hint is not None:      # float32 [E, N], persistent between steps: starting thresholds of the search
+        assert nbr_hint.dtype == np.float32 and nbr_hint.flags["C_CONTIGUOUS"]
+        a.nbr_hint = _ptr(nbr_hint)
+        a.hint_slack = f32(2.5) * f32(params["max_speed"]) * dt + f32(1e-4)
     if world is not None and world.nv > 0:
         a.vert_pd, a.vert_link, a.bsp, a.bsp_seg = _ptr(world.pd), _ptr(world.link), _ptr(world.bsp), _ptr(world.seg)
         a.shared_nodes, a.vert_stride = world.nv, 0

@@ -60,6 +60,7 @@ void run_k(const orca::StepArgs& a, int policy) {
       src.env_vel = svel.data();
       src.n = N;
       src.self = i;
+      src.full_range_sq = a.nd_sq;
       if (tile_grid) {
         src.cell_start = cell_start.data();
         src.sorted = sorted.data();
@@ -119,7 +120,7 @@ void run_grid_k(const orca::StepArgs& a0, int policy) {
   for (int j = 0; j < T; ++j) {
     const int g = sidx[(size_t)j], env = g / N, la = g - env * N;
     orca::GridSource src;
-    src.spv = spv.data(); src.orig = sidx.data(); src.cell_start = start.data();
+    src.spv = spv.data(); src.orig = sidx.data(); src.cell_start = start.data(); src.full_range_sq = a.nd_sq;
     src.gp = gp; src.env = env; src.env_n0 = env * N; src.self = j;
     orca::Lines L; L.base = lines.data(); L.stride = 1;
     const int es = estep0[(size_t)env];

@@ -10,15 +10,23 @@ from _common import goal_pref, neighbor_sets_equal_up_to_ties, oracle_sims, pill
 from collision_avoidance_b200 import scenarios
 
 
-def _compare(scn, steps, grid=False, sample_stride=1):
+def _compare(scn, steps, grid=False, sample_stride=1, hint=False, teleport_every=0):
     P = snake(scn.params)
+    hints = np.full((scn.num_envs, 1, scn.agents_per_env), 3.0e38, np.float32) if hint else None
+    rng = np.random.default_rng(5)
     polys = scn.obstacles
     worlds = [_emul.World(p) for p in polys] if scn.per_env_obstacles else [_emul.World(polys)] * scn.num_envs
     sims = oracle_sims(scn)
     E, N = scn.num_envs, scn.agents_per_env
     worst = 0.0
     stats = np.zeros(8, np.uint64)
-    for _ in range(steps):
+    for t in range(steps):
+        if teleport_every and t % teleport_every == teleport_every - 1:
+            for s in sims:      # the caller moves agents between steps: the stored thresholds are stale
+                p = s.positions()
+                idx = rng.choice(N, N // 4, replace=False)
+                p[idx] = rng.uniform(0.2 * scn.envsize, 0.8 * scn.envsize, (len(idx), 2)).astype(np.float32)
+                s.set_positions(p)
         pos = np.stack([s.positions() for s in sims])
         vel = np.stack([s.velocities() for s in sims])
         pref = goal_pref(pos, scn.goal).astype(np.float32)
@@ -28,7 +36,7 @@ def _compare(scn, steps, grid=False, sample_stride=1):
         for e in range(E):  # one world at a time (each may own its obstacles)
             pe, ve = pos[e:e + 1].copy(), vel[e:e + 1].copy()
             out = _emul.emul_step(P, pe, ve, policy=0, pref=np.ascontiguousarray(pref[e:e + 1]), world=worlds[e],
-                                  want_neighbors=True, stats=stats, grid=grid)
+                                  want_neighbors=True, stats=stats, grid=grid, nbr_hint=None if hints is None else hints[e])
             op, ov = sims[e].positions(), sims[e].velocities()
             assert float(np.abs(pe[0] - op).max()) <= 1e-4 and float(np.abs(ve[0] - ov).max()) <= 1e-4
             for i in range(0, N, sample_stride):
@@ -230,3 +238,18 @@ def test_uncapped_obstacle_path_matches_the_oracle():
             most_lines = max(most_lines, sims[0].orca_lines(i)[1])
     assert most_nbrs > 16 and most_lines > 6, (most_nbrs, most_lines)
     assert stats[4] == 0          # ORCA_STAT_OVERFLOW: nothing exceeded the slow path
+
+
+def test_search_from_last_steps_kth_distance_is_exact():
+    """The threshold searches (in-block grid, uniform grid) start from last step's k-th neighbor
+    distance + what two agents can approach in one step.  Same lists, same bits as the oracle --
+    also when the caller teleports a quarter of the agents between steps (stale thresholds: the lane
+    searches again from the full range)."""
+    worst, _ = _compare(scenarios.crowd(2, 60, seed=21, blocks=4), steps=50, hint=True)
+    assert worst == 0.0
+    worst, _ = _compare(scenarios.crowd(1, 80, seed=22), steps=40, hint=True, teleport_every=5)
+    assert worst == 0.0
+    worst, _ = _compare(scenarios.crowd(1, 500, seed=23), steps=10, grid=True, sample_stride=5, hint=True)
+    assert worst == 0.0
+    worst, _ = _compare(scenarios.crowd(1, 400, seed=24), steps=12, grid=True, sample_stride=5, hint=True, teleport_every=4)
+    assert worst == 0.0
