@@ -10,6 +10,8 @@
 #include <cmath>
 #include <cstdint>
 #include <utility>
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 namespace orca_host {
@@ -167,6 +169,58 @@ inline void process(ObstacleTables& T) {
   std::vector<int> all(static_cast<size_t>(T.num_vertices()));
   for (size_t i = 0; i < all.size(); ++i) all[i] = static_cast<int>(i);
   detail::Builder(T).build(all, 0);
+}
+
+// Obstacle-free map of a processed world: a kCullGrid x kCullGrid grid over the bounding box of all
+// obstacle vertices; bit (cx, cy) is set when some edge MAY come within `range` of a point of the
+// cell (distance from the cell's centre to the edge <= range + the cell's half diagonal, plus 5 % of a
+// cell for the rounding of the cell lookup).  A clear bit proves that an agent in that cell has no
+// obstacle neighbor, so the kernel skips the BSP walk (RVO2's result -- an empty list -- unchanged).
+constexpr int kCullGrid = 32;
+struct CullMap {
+  uint32_t rows[kCullGrid];  // rows[cy] bit cx
+  float x0, y0, inv_cx, inv_cy;
+};
+inline CullMap build_cull_map(const ObstacleTables& T, float range) {
+  CullMap M;
+  for (int i = 0; i < kCullGrid; ++i) M.rows[i] = 0xffffffffu;
+  M.x0 = M.y0 = 0.f;
+  M.inv_cx = M.inv_cy = 0.f;  // inv = 0: every point maps outside -> always walk
+  const int V = T.num_vertices();
+  if (V == 0) return M;
+  double bx0 = T.px[0], bx1 = T.px[0], by0 = T.py[0], by1 = T.py[0];
+  for (int v = 1; v < V; ++v) {
+    bx0 = std::min<double>(bx0, T.px[v]);
+    bx1 = std::max<double>(bx1, T.px[v]);
+    by0 = std::min<double>(by0, T.py[v]);
+    by1 = std::max<double>(by1, T.py[v]);
+  }
+  const double cw = (bx1 - bx0) / kCullGrid, ch = (by1 - by0) / kCullGrid;
+  if (!(cw > 0.0) || !(ch > 0.0)) return M;
+  const double reach = (double)range + 0.5 * std::sqrt(cw * cw + ch * ch) + 0.05 * std::max(cw, ch);
+  for (int cy = 0; cy < kCullGrid; ++cy) {
+    uint32_t bits = 0u;
+    for (int cx = 0; cx < kCullGrid; ++cx) {
+      const double qx = bx0 + (cx + 0.5) * cw, qy = by0 + (cy + 0.5) * ch;
+      bool near = false;
+      for (int v = 0; v < V && !near; ++v) {
+        const int w = T.next[v];
+        const double ax = T.px[v], ay = T.py[v], ex = T.px[w] - ax, ey = T.py[w] - ay;
+        const double len2 = ex * ex + ey * ey;
+        double t = len2 > 0.0 ? ((qx - ax) * ex + (qy - ay) * ey) / len2 : 0.0;
+        t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+        const double dx = qx - (ax + t * ex), dy = qy - (ay + t * ey);
+        near = dx * dx + dy * dy <= reach * reach;
+      }
+      bits |= near ? (1u << cx) : 0u;
+    }
+    M.rows[cy] = bits;
+  }
+  M.x0 = (float)bx0;
+  M.y0 = (float)by0;
+  M.inv_cx = (float)(1.0 / cw);
+  M.inv_cy = (float)(1.0 / ch);
+  return M;
 }
 
 }  // namespace orca_host

@@ -90,6 +90,8 @@ struct OrcaSim {
   int4* d_bsp = nullptr;
   float4* d_bsp_seg = nullptr;
   int* d_env_nodes = nullptr;
+  uint32_t* d_cull_rows = nullptr;  // obstacle-free maps (obstacle_world.h: build_cull_map), 32 words per world
+  float4* d_cull_geo = nullptr;
   int shared_nodes = 0;
   int vert_stride = 0;
   // staging for the *_host entry points
@@ -126,6 +128,10 @@ void free_obstacles(OrcaSim* s) {
   cudaFree(s->d_bsp);
   cudaFree(s->d_bsp_seg);
   cudaFree(s->d_env_nodes);
+  cudaFree(s->d_cull_rows);
+  cudaFree(s->d_cull_geo);
+  s->d_cull_rows = nullptr;
+  s->d_cull_geo = nullptr;
   s->d_vert_pd = nullptr;
   s->d_vert_link = nullptr;
   s->d_bsp = nullptr;
@@ -166,6 +172,8 @@ void fill_common(const OrcaSim* s, orca::StepArgs* a) {
   a->vert_stride = s->per_env ? s->vert_stride : 0;
   a->world_verts = s->vert_stride;
   a->world_slots = 0;
+  a->cull_rows = s->d_cull_rows;
+  a->cull_geo = s->d_cull_geo;
 }
 
 template <int K, bool KFULL, int POLICY, int OL>
@@ -415,6 +423,21 @@ int orca_set_obstacles(OrcaSim* s, const float* xy, const int32_t* poly_sizes, i
   }
   s->shared_nodes = s->per_env ? 0 : nodes[0];
   s->vert_stride = stride;
+  // obstacle-free maps: where no edge can come within the obstacle range, the step skips the BSP walk
+  if (std::getenv("ORCA_B200_NO_OBST_CULL") == nullptr) {
+    const float orange = s->p.time_horizon_obst * s->p.max_speed + s->p.radius;
+    std::vector<uint32_t> rows((size_t)n_worlds * orca_host::kCullGrid);
+    std::vector<float4> geo((size_t)n_worlds);
+    for (int w = 0; w < n_worlds; ++w) {
+      const orca_host::CullMap M = orca_host::build_cull_map(s->worlds[(size_t)w], orange);
+      std::memcpy(&rows[(size_t)w * orca_host::kCullGrid], M.rows, sizeof(M.rows));
+      geo[(size_t)w] = make_float4(M.x0, M.y0, M.inv_cx, M.inv_cy);
+    }
+    CUDA_TRY(cudaMalloc(&s->d_cull_rows, rows.size() * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&s->d_cull_geo, geo.size() * sizeof(float4)));
+    CUDA_TRY(cudaMemcpy(s->d_cull_rows, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(s->d_cull_geo, geo.data(), geo.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  }
   return ORCA_OK;
 }
 

@@ -144,6 +144,12 @@ struct Lines {
 ORCA_HD float2 pt(float4 l) { return v2(l.x, l.y); }
 ORCA_HD float2 dr(float4 l) { return v2(l.z, l.w); }
 
+#if defined(__CUDA_ARCH__)
+#define ORCA_LDG(p) __ldg(p)  // read-only global data
+#else
+#define ORCA_LDG(p) (*(p))
+#endif
+
 // ---- processed obstacle world of one env ---------------------------------------------------
 // vert_pd[v]   = (point.x, point.y, unitDir.x, unitDir.y)
 // vert_link[v] = (next, prev, isConvex, 0)
@@ -156,13 +162,20 @@ struct ObstacleWorld {
   const int4* bsp;
   const float4* bsp_seg;
   int n_nodes;
+  // obstacle-free map (obstacle_world.h: build_cull_map): 32 rows of 32 bits over the box that starts at
+  // (geo.x, geo.y) with 1 / cell size (geo.z, geo.w); nullptr: none
+  const uint32_t* cull_rows;
+  float4 cull_geo;
 };
 
-#if defined(__CUDA_ARCH__)
-#define ORCA_LDG(p) __ldg(p)  // read-only global data
-#else
-#define ORCA_LDG(p) (*(p))
-#endif
+// May an agent at p have an obstacle neighbor at all?  false = provably not (skip the BSP walk).
+ORCA_HD bool obstacles_may_be_near(const ObstacleWorld& W, float2 p) {
+  if (W.cull_rows == nullptr) return true;
+  const float fx = (p.x - W.cull_geo.x) * W.cull_geo.z, fy = (p.y - W.cull_geo.y) * W.cull_geo.w;
+  if (!(fx >= 0.f && fx < 32.f && fy >= 0.f && fy < 32.f)) return true;  // outside the mapped box (or NaN): walk
+  return ((ORCA_LDG(&W.cull_rows[(int)fy]) >> (int)fx) & 1u) != 0u;
+}
+
 // obstacle tables may sit in global OR shared memory (staged by the tile kernel): generic load
 #define ORCA_LD(p) (*(p))
 

@@ -98,6 +98,7 @@ inline void grid_free(GridScratch& g) {
 // Candidates of an agent = agents in the 3 x 3 cells around it, read from the cell-sorted
 // snapshot.  Entries are identified by their sorted slot; `orig` maps a slot to the agent id.
 struct GridSource {
+  static constexpr bool kObstacleCull = true;
   const float4* spv;  // (pos, vel) per sorted slot
   const int* orig;
   const int* cell_start;
@@ -529,7 +530,8 @@ __global__ void __launch_bounds__(ORCA_GRID_TPB, (OL <= 2 ? 1024 : 768) / ORCA_G
     c.p = v2(pv.x, pv.y);
     c.v = v2(pv.z, pv.w);
     if (!a.neighbors_only) c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];
-    alive = agent_front<K, KFULL, POLICY, OL>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c);
+    const ObstacleWorld W = global_world_with_cull(a, env);
+    alive = agent_front<K, KFULL, POLICY, OL>(a, env, g, estep, src, W, L, warp_mask, c);
   }
   if (a.neighbors_only) return;  // uniform over the grid
   block_lp3<K>(s_lines, s_pool, s_meta, s_nv, s_queue, s_warp_cnt, alive && !c.overflow && c.fail < c.n, c, a.vmax);

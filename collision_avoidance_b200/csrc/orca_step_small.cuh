@@ -100,6 +100,9 @@ struct StepArgs {
   // distance: what two agents can approach each other within one step, 2 * maxSpeed * timeStep + 25 %
   float* nbr_hint;
   float hint_slack;
+  // obstacle-free maps: 32 row words + one float4 of geometry per world (stride 0 when the world is shared)
+  const uint32_t* cull_rows;
+  const float4* cull_geo;
 };
 
 // Where an agent's neighbor candidates come from.  TileSource: the pre-step snapshot of the
@@ -115,7 +118,11 @@ constexpr int kTileGrid = 8;                          // cells per side
 constexpr int kTileCells = kTileGrid * kTileGrid;     // 64
 constexpr int kTileStartStride = kTileCells + 2;      // cell_start row per env (u16), padded
 
-struct TileSource {
+// SMALL = the kernel only ever sees worlds of at most 32 agents (the slim kernel): the candidate-buffer
+// and in-block-grid searches, and the threshold hint with them, are not compiled at all.
+template <bool SMALL>
+struct TileSourceT {
+  static constexpr bool kObstacleCull = false;
   const float2* env_pos;
   const float2* env_vel;
   int n;
@@ -265,7 +272,7 @@ struct TileSource {
   }
   // true when gather() searches through the candidate buffer with a shrinking threshold and knows how
   // to search again: it can start from a tighter threshold than the neighbor range (see agent_front)
-  ORCA_HD bool threshold_search() const { return cell_start != nullptr; }
+  ORCA_HD bool threshold_search() const { return !SMALL && cell_start != nullptr; }
   float full_range_sq = 0.f;  // the neighbor range (squared), for the second pass
   // The list arrives initialised with its STARTING threshold (agent_front): nk.range_sq, the neighbor
   // range or last step's tighter bound.  The threshold paths search again from the full range
@@ -277,7 +284,7 @@ struct TileSource {
       gather_ranked<16>(nk, p, scratch);
       return;
     }
-    if (n <= 32) {
+    if (SMALL || n <= 32) {
 #ifdef ORCA_RANKED32_FLAT  // A/B switch: all 32 keys in registers
       gather_ranked<32>(nk, p, scratch);
 #else
@@ -365,6 +372,7 @@ struct TileSource {
   ORCA_HD float2 vel(int q) const { return env_vel[q]; }
   ORCA_HD int local_id(int q) const { return q; }
 };
+using TileSource = TileSourceT<false>;
 
 // atomics: device atomics in the kernels, plain adds in the single-threaded host emulation
 ORCA_HD void stat_add_u64(unsigned long long* stats, int slot, unsigned long long v) {
@@ -448,6 +456,17 @@ ORCA_HD ObstacleWorld global_world(const StepArgs& a, int env) {
   W.bsp = a.bsp + voff;
   W.bsp_seg = a.bsp_seg + voff;
   W.n_nodes = (a.env_nodes != nullptr) ? a.env_nodes[env] : a.shared_nodes;
+  W.cull_rows = nullptr;
+  return W;
+}
+// ... plus the obstacle-free map of the env's world (obstacle_world.h: build_cull_map), for the sources that use it
+ORCA_HD ObstacleWorld global_world_with_cull(const StepArgs& a, int env) {
+  ObstacleWorld W = global_world(a, env);
+  if (a.cull_rows != nullptr) {
+    const size_t w = (a.vert_stride > 0) ? (size_t)env : 0;
+    W.cull_rows = a.cull_rows + w * 32;
+    W.cull_geo = ORCA_LDG(&a.cull_geo[w]);
+  }
   return W;
 }
 
@@ -528,7 +547,11 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
   float od[ORCA_MAX_OBST_NEIGHBORS];
   int oid[ORCA_MAX_OBST_NEIGHBORS];
   int ocnt = 0;
-  if (W.n_nodes > 0) obstacle_neighbors(W, p, a.obst_range_sq, od, oid, &ocnt, &overflow);
+  // (the obstacle-free map pays where warps are spatially coherent and the world is mostly empty: the
+  // uniform-grid kernel, 367 -> 357 us in config 5; in the tile kernels it measured 0 to +3.5 %, so they
+  // do not compile the lookup)
+  if (W.n_nodes > 0 && (!Src::kObstacleCull || obstacles_may_be_near(W, p)))
+    obstacle_neighbors(W, p, a.obst_range_sq, od, oid, &ocnt, &overflow);
 
   // Temporal coherence: where the search runs on a shrinking threshold (candidate buffer paths), it
   // starts from last step's k-th neighbor distance plus what two agents can approach each other in one
@@ -825,7 +848,8 @@ ORCA_HD void agent_step_body(const StepArgs& a, const int env, const int la, con
   c.p = p;
   c.v = v;
   c.aim = (POLICY == POLICY_EXTERNAL) ? a.pref[g] : a.goal[g];
-  if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, global_world(a, env), L, warp_mask, c)) return;
+  const ObstacleWorld W = Src::kObstacleCull ? global_world_with_cull(a, env) : global_world(a, env);
+  if (!agent_front<K, KFULL, POLICY>(a, env, g, estep, src, W, L, warp_mask, c)) return;
   if (c.overflow)
     apply_slow_result(agent_slow_path<K, KFULL>(slow_params(a), src, global_world(a, env), L, K + ORCA_MAX_OBST_LINES, warp_mask,
                                                 c.p, c.v, c.pref), c);
@@ -989,8 +1013,9 @@ __device__ __forceinline__ float tile_ordered_to_float(int i) { return __int_as_
 // the last cell are clamped into it (a superset of the 3 x 3 neighborhood, never a subset).
 // The order of ids inside a cell depends on the order of the atomics; the neighbor list does not
 // (equal distances are ranked by id).  Called by every thread of the block.
+template <class Src>
 __device__ __forceinline__ void build_tile_grid(const StepArgs& a, void* area, const bool valid, const int le, const int la,
-                                                const float2 p, TileSource& src) {
+                                                const float2 p, Src& src) {
   const int tid = threadIdx.x, tpb = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = tpb >> 5;
   const int envs = a.envs_per_block;
   int* cnt = reinterpret_cast<int*>(area);
@@ -1075,7 +1100,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, (OL <= 2 ? 4 : ORCA_STE
   const int env = env0 + le;
   const bool valid = (le < a.envs_per_block) && (env < a.E);
   int g = env * N + la;
-  const bool tile_grid = a.tile_grid_inv_cell > 0.f;  // uniform over the grid
+  const bool tile_grid = !(OL <= 2) && a.tile_grid_inv_cell > 0.f;  // uniform over the grid; never in the slim kernel
 
   AgentCarry c;
   c.p = v2(0.f, 0.f);
@@ -1115,7 +1140,8 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, (OL <= 2 ? 4 : ORCA_STE
   __syncthreads();
   const unsigned warp_mask = __ballot_sync(0xffffffffu, valid);  // lanes that run the step
   bool alive = valid;
-  TileSource src;
+  using Source = TileSourceT<(OL <= 2)>;  // the slim kernel is launched for worlds of at most 32 agents only
+  Source src;
   if (tile_grid) {
     build_tile_grid(a, s_nv, valid, le, la, c.p, src);
     // From here on the thread works on the la-th agent of its env IN CELL ORDER instead of agent la:
@@ -1167,7 +1193,7 @@ __global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, (OL <= 2 ? 4 : ORCA_STE
     Lines L;
     L.base = s_lines + tid;
     L.stride = tpb;
-    TileSource scan;
+    Source scan;
     scan.env_pos = s_pos + le * N;
     scan.env_vel = s_vel + le * N;
     scan.n = N;

@@ -34,7 +34,7 @@ class StepArgs(ctypes.Structure):
         ("vert_pd", c_p), ("vert_link", c_p), ("bsp", c_p), ("bsp_seg", c_p), ("env_nodes", c_p),
         ("shared_nodes", c_i), ("vert_stride", c_i), ("world_slots", c_i), ("world_verts", c_i), ("neighbors_only", c_i), ("grid_path", c_i),
         ("pos_mirror", c_p), ("vel_mirror", c_p), ("tile_grid_inv_cell", c_f),
-        ("nbr_hint", c_p), ("hint_slack", c_f),
+        ("nbr_hint", c_p), ("hint_slack", c_f), ("cull_rows", c_p), ("cull_geo", c_p),
     ]
 
 
@@ -84,7 +84,8 @@ def _ptr(a):
 class World:
     """Processed obstacle tables of one shared world (host arrays)."""
 
-    def __init__(self, polygons):
+    def __init__(self, polygons, obst_range=2.0):
+        """obst_range = timeHorizonObst * maxSpeed + radius (2.0 for every world of the reference)."""
         L = lib()
         xy = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32).reshape(-1, 2) for p in polygons])
                                   if polygons else np.zeros((0, 2), np.float32))
@@ -95,9 +96,12 @@ class World:
         self.bsp = np.zeros((max_v, 4), np.int32)
         self.seg = np.zeros((max_v, 4), np.float32)
         depth = c_i(0)
+        self.cull_rows = np.zeros(32, np.uint32)
+        self.cull_geo = np.zeros(4, np.float32)
         nv = L.emul_build_world(c_p(xy.ctypes.data), c_p(sizes.ctypes.data), len(polygons), max_v,
                                 c_p(self.pd.ctypes.data), c_p(self.link.ctypes.data), c_p(self.bsp.ctypes.data),
-                                c_p(self.seg.ctypes.data), ctypes.byref(depth))
+                                c_p(self.seg.ctypes.data), ctypes.byref(depth), c_f(obst_range),
+                                c_p(self.cull_rows.ctypes.data), c_p(self.cull_geo.ctypes.data))
         assert nv >= 0, nv
         self.nv = nv
         self.depth = depth.value
@@ -164,6 +168,7 @@ def emul_step(params, pos, vel, *, policy=0, pref=None, goal=None, goal2=None, w
     if world is not None and world.nv > 0:
         a.vert_pd, a.vert_link, a.bsp, a.bsp_seg = _ptr(world.pd), _ptr(world.link), _ptr(world.bsp), _ptr(world.seg)
         a.shared_nodes, a.vert_stride = world.nv, 0
+        a.cull_rows, a.cull_geo = _ptr(world.cull_rows), _ptr(world.cull_geo)
     a.neighbors_only = 1 if neighbors_only else 0
     rc = lib().emul_step_grid(ctypes.byref(a), policy) if grid else lib().emul_step(ctypes.byref(a), policy)
     assert rc == 0

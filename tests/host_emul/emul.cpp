@@ -140,7 +140,7 @@ extern "C" {
 // Mirrors orca_set_obstacles + the table packing of orca_api.cu for ONE shared world.
 // Returns number of vertices; fills pd[v*4], link[v*4], bsp[v*4] (caller allocates max_v rows).
 int emul_build_world(const float* xy, const int* poly_sizes, int num_polys, int max_v, float* pd, int* link, int* bsp,
-                     float* seg, int* depth) {
+                     float* seg, int* depth, float obst_range, unsigned* cull_rows, float* cull_geo) {
   orca_host::ObstacleTables T;
   size_t off = 0;
   for (int p = 0; p < num_polys; ++p) {
@@ -158,6 +158,9 @@ int emul_build_world(const float* xy, const int* poly_sizes, int num_polys, int 
     seg[4 * v] = T.px[e1]; seg[4 * v + 1] = T.py[e1]; seg[4 * v + 2] = T.px[e2]; seg[4 * v + 3] = T.py[e2];
   }
   *depth = T.depth;
+  const orca_host::CullMap M = orca_host::build_cull_map(T, obst_range);
+  for (int i = 0; i < orca_host::kCullGrid; ++i) cull_rows[i] = M.rows[i];
+  cull_geo[0] = M.x0; cull_geo[1] = M.y0; cull_geo[2] = M.inv_cx; cull_geo[3] = M.inv_cy;
   return nv;
 }
 
