@@ -624,9 +624,23 @@ int orca_observe(OrcaSim* s, const float* pos_dev, const float* vel_dev, const f
   }
   const long long total = (long long)s->E * s->N * laser_num;
   if (total >= (1ll << 31)) return fail(ORCA_ERR_UNSUPPORTED, "orca_observe: E * N * laser_num must be below 2^31");
-  const int apb = orca::obs_agents_per_block(laser_num);  // whole agents per block: their rays share staged data
-  const long long blocks = ((long long)s->E * s->N + apb - 1) / apb;
-  orca::observe_kernel<<<(unsigned)blocks, orca::kObsThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, apb);
+  const bool paired = orca::obs_table_is_antipodal(a);  // ray i + R / 2 = -ray i: one lane culls for both
+  const orca::ObsPlan plan = orca::obs_plan(a, paired);
+  const size_t smem = (size_t)plan.warp_bytes * orca::kObsWarps;
+  {
+    static std::atomic<bool> attr_set[orca::kMaxDevices];  // function attributes are per device
+    if (s->device >= orca::kMaxDevices || !attr_set[s->device].load(std::memory_order_acquire)) {
+      CUDA_TRY(cudaFuncSetAttribute(orca::observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(orca::observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      if (s->device < orca::kMaxDevices) attr_set[s->device].store(true, std::memory_order_release);
+    }
+  }
+  const long long per_block = (long long)plan.A * orca::kObsWarps;  // whole agents per warp: their rays share staged data
+  const long long blocks = ((long long)s->E * s->N + per_block - 1) / per_block;
+  if (paired)
+    orca::observe_kernel<true><<<(unsigned)blocks, orca::kObsThreads, smem, static_cast<cudaStream_t>(stream)>>>(a, plan);
+  else
+    orca::observe_kernel<false><<<(unsigned)blocks, orca::kObsThreads, smem, static_cast<cudaStream_t>(stream)>>>(a, plan);
   CUDA_TRY(cudaGetLastError());
   s->launches += 1;
   return ORCA_OK;

@@ -70,3 +70,19 @@ def test_product_code_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "rvo2_oracle" not in src, f
+
+
+def test_library_has_no_viaddmnmx_with_a_uniform_operand():
+    """ptxas 12.9.86 (sm_100a) fuses min(uniform - x, y) into `VIADDMNMX R, R, UR, R` without a
+    negate bit, i.e. min(uniform + x, y) (tools/probes/viaddmnmx_probe.cu; it made the observation
+    kernel's last chunk run past the batch).  The shipped library must not contain that form."""
+    import re
+    import shutil
+    import subprocess
+    from collision_avoidance_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(build.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not here")
+    sass = subprocess.run([cuobjdump, "-sass", build.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    bad = [l.strip() for l in sass.splitlines() if re.search(r"VIADDMNMX(\.\w+)* R\d+, R\d+, UR\d+", l)]
+    assert not bad, bad[:3]

@@ -245,6 +245,32 @@ def test_observation_kernel_equals_its_host_twin(R, C):
     assert hits > 0 or R == 1
 
 
+@pytest.mark.parametrize("E", [1, 23, 64, 320])
+def test_observation_of_the_gym_world_equals_its_host_twin(E):
+    """The gym world (10 agents, k = 5, radius 0.5 of 1.5: large polygons, many (ray, neighbor) pairs,
+    shared obstacles) at batch sizes whose last warp chunk is partial -- 640 and 3,200 agents are the
+    sizes at which a ptxas miscompile of the chunk bound once ran past the end of the batch (see
+    observe_kernel) -- against the serial host twin, bit for bit, walls and blocks included."""
+    import torch
+    import _emul
+    from _common import snake
+    from collision_avoidance_b200 import envs
+    env = envs.Collision_Avoidance_Env(numAgents=10, num_envs=E, seed=3)
+    theta = (torch.rand(E, 10, device="cuda", generator=torch.Generator("cuda").manual_seed(5)) - 0.5) * 0.6
+    for _ in range(40):
+        env.step(theta)
+    obs = env.obs.cpu().numpy()
+    pos, vel, goal = env.sim.pos.cpu().numpy(), env.sim.vel.cpu().numpy(), env.targets_pos.cpu().numpy()
+    nbr = {"nbr_idx": np.ascontiguousarray(env.sim.nbr_idx.cpu().numpy()),
+           "nbr_cnt": np.ascontiguousarray(env.sim.nbr_cnt.cpu().numpy()),
+           "onbr_idx": np.ascontiguousarray(env.sim.obst_nbr_idx.cpu().numpy()),
+           "onbr_cnt": np.ascontiguousarray(env.sim.obst_nbr_cnt.cpu().numpy())}
+    ref = _emul.emul_observe(snake(env.scn.params), pos, vel, goal, nbr, world=_emul.World(env.scn.obstacles))
+    assert np.array_equal(ref, obs), float(np.abs(ref - obs).max())
+    assert (np.abs(ref).reshape(-1, 4)[:, :2].sum(-1) > 0).sum() > E  # rays do hit things
+    assert nbr["onbr_cnt"].max() > 0
+
+
 def test_handles_on_two_devices_in_one_process():
     """Kernel attributes (dynamic shared memory opt-in) are per device: a second handle on another
     GPU of the same process must launch just like the first.  Skipped on single-GPU boxes."""
