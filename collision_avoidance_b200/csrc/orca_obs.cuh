@@ -190,8 +190,8 @@ ORCA_HD unsigned long long pair_test(const float2* poly, int C, float2 rel, floa
     float f_prev = f_first;
     for (int m = 1; m <= C; ++m) {
       const float f_cur = (m < C) ? det(ew, add(poly[m], rel)) : f_first;
-      const bool one_side = (f_prev > kObsSideEps && f_cur > kObsSideEps) || (f_prev < -kObsSideEps && f_cur < -kObsSideEps);
-      const bool clear_exit = flt.drop_exit && fabsf(f_prev) > flt.clear_eps && fabsf(f_cur) > flt.clear_eps && ((f_cur > 0.f) == flt.ccw);
+      const bool one_side = fminf(f_prev, f_cur) > kObsSideEps || fmaxf(f_prev, f_cur) < -kObsSideEps;
+      const bool clear_exit = flt.drop_exit && fminf(fabsf(f_prev), fabsf(f_cur)) > flt.clear_eps && ((f_cur > 0.f) == flt.ccw);
       edges |= (one_side || clear_exit) ? 0u : (1u << (m - 1));
       f_prev = f_cur;
     }
@@ -214,11 +214,19 @@ ORCA_HD unsigned long long pair_test(const float2* poly, int C, float2 rel, floa
   return best;
 }
 
+// The ray parameter of a segment ray_hit_t has already accepted: the same two expressions, no tests.
+ORCA_HD float ray_t_of_hit(float2 e, float2 p2, float2 p3) {
+  const float bx = p3.x - p2.x, by = p3.y - p2.y;
+  const float denom = e.x * by - bx * e.y;
+  const float cx = -p2.x, cy = -p2.y;
+  const float t_num = bx * cy - by * cx;
+  return t_num / denom;
+}
+
 // Phase C: the observation row entry of a ray whose winner is edge m of the polygon around `rel`
 // (neighbor velocity nv, rotated into the agent's frame) / obstacle edge `ed`.
 ORCA_HD float4 ray_result_polygon(const float2* poly, int C, float2 rel, float2 nv, float c, float s, float2 e, float2 ew, int m) {
-  float t = 0.f;
-  ray_hit_t(ew, add(poly[m - 1], rel), add(poly[m < C ? m : 0], rel), &t);
+  const float t = ray_t_of_hit(ew, add(poly[m - 1], rel), add(poly[m < C ? m : 0], rel));
   float4 out;
   out.x = t * e.x;
   out.y = t * e.y;
@@ -227,8 +235,7 @@ ORCA_HD float4 ray_result_polygon(const float2* poly, int C, float2 rel, float2 
   return out;
 }
 ORCA_HD float4 ray_result_edge(float4 ed, float2 e, float2 ew) {
-  float t = 0.f;
-  ray_hit_t(ew, v2(ed.x, ed.y), v2(ed.z, ed.w), &t);
+  const float t = ray_t_of_hit(ew, v2(ed.x, ed.y), v2(ed.z, ed.w));
   float4 out;
   out.x = t * e.x;
   out.y = t * e.y;
@@ -298,8 +305,12 @@ ORCA_HD float4 observe_ray(const ObsArgs& a, int g, int ray) {
 //   rows     after the last pass the rest of the queue is drained and the rows are written (float4
 //            per ray, 128 contiguous bytes per agent and store).
 // Only __syncwarp() orders the phases.
+#ifndef ORCA_OBS_BLOCKS_PER_SM
+#define ORCA_OBS_BLOCKS_PER_SM 5  // measured per 1 M agents: 4 blocks 291 us, 5 blocks 274 us, 6 blocks (40 registers, spills) 285 us
+#endif
 constexpr int kObsWarps = 8;
 constexpr int kObsThreads = kObsWarps * 32;
+constexpr int kObsWarpBytes = ((227 * 1024) / ORCA_OBS_BLOCKS_PER_SM - 1024 - 640) / kObsWarps;  // shared memory a warp may use
 constexpr int kObsQueue = 64;      // < 32 pending before a push round, at most 32 pushed per round
 constexpr int kObsEdgeSlots = 4;   // obstacle edges staged per agent; further ones are read from global memory
 
@@ -342,9 +353,9 @@ inline ObsPlan obs_plan(const ObsArgs& a, bool paired) {
   p.AP = 32 / p.L;
   p.logKP = obs_log2_ceil(a.k);
   p.KP = 1 << p.logKP;
-  // chunk size: what fits 7 KB per warp (four blocks of 8 warps per SM), at most 32 agents (lane = agent
+  // chunk size: what fits a warp's share of shared memory (five blocks of 8 warps per SM: 5.5 KB), at most 32 agents (lane = agent
   // while staging; 5 bits of a queue entry), in whole passes, even (16-byte alignment of the edge array)
-  p.A = (7168 - kObsQueue * 2) / obs_bytes_per_agent(a.R, p.KP);
+  p.A = (kObsWarpBytes - kObsQueue * 2) / obs_bytes_per_agent(a.R, p.KP);
   if (p.A > 32) p.A = 32;
   p.A -= p.A % p.AP;
   if (p.A < p.AP) p.A = p.AP;
@@ -413,7 +424,7 @@ __device__ __forceinline__ void obs_drain(const ObsArgs& a, const ObsPlan& p, co
 }
 
 template <bool PAIRED>
-__global__ void __launch_bounds__(kObsThreads, 4) observe_kernel(const ObsArgs a, const ObsPlan p) {
+__global__ void __launch_bounds__(kObsThreads, ORCA_OBS_BLOCKS_PER_SM) observe_kernel(const ObsArgs a, const ObsPlan p) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ float4 s_ray[ORCA_MAX_LASER];  // (e.x, e.y, |e|, 1 / |e|)
   __shared__ float2 s_poly[ORCA_MAX_CIRCLE_APPROX];
