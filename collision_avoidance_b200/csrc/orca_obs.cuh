@@ -24,8 +24,8 @@
 //            makes its whole warp wait for the ray with the most of them): find the edges whose
 //            endpoints straddle the ray line (bit mask over the C edges), exact
 //            line_intersection only for those.  Hits go back to the owning ray through a 64-bit
-//            atomicMin on (distance bits, item, edge) in shared memory;
-//   phase C  the ray's thread recomputes the winning edge's hit and writes its float4 of the row
+//            atomicMin on (ray-parameter bits, item, edge) in shared memory;
+//   phase C  the ray's thread turns the winning key (it holds t) into its float4 of the row
 //            (coalesced).
 // Ties keep the first segment in the reference's order (neighbors in list order, edges in ring
 // order, then obstacle edges): the order index is the low word of the key.
@@ -117,11 +117,13 @@ ORCA_HD float2 agent_frame(const ObsArgs& a, int g) {
 // ray end in the world frame (relative to the agent): inverse rotation (x, y) -> (c x + s y, -s x + c y)
 ORCA_HD float2 ray_world(float c, float s, float2 e) { return v2(c * e.x + s * e.y, c * e.y - s * e.x); }
 
-ORCA_HD unsigned long long hit_key(float2 e, float t, int item, int edge) {
-  const float hx = t * e.x, hy = t * e.y;
-  const float d = sqrtf(hx * hx + hy * hy);
-  return ((unsigned long long)(unsigned)float_to_bits(d) << 32) | (unsigned)((item << 5) | edge);
+// Key of a hit: (bits of the ray parameter t, item, edge).  All hits of a key's ray lie on that ray,
+// so their distance t * |e| orders like t (t in [0, 1]: non-negative floats order like their bit
+// patterns); keeping t itself, not the distance, lets the row be written from the key alone.
+ORCA_HD unsigned long long hit_key(float t, int item, int edge) {
+  return ((unsigned long long)(unsigned)float_to_bits(fabsf(t)) << 32) | (unsigned)((item << 5) | edge);
 }
+ORCA_HD float hit_key_t(unsigned long long key) { return bits_to_float((int)(unsigned)(key >> 32)); }
 
 // Phase A, agent neighbors: bit q = neighbor q's polygon may be hit by the ray (e: agent frame,
 // ew: world frame).
@@ -151,7 +153,7 @@ ORCA_HD unsigned long long obstacle_hits(const AgentScan& A, float2 e, float2 ew
     const float4 ed = A.edge[q];
     float t;
     if (ray_hit_t(ew, v2(ed.x, ed.y), v2(ed.z, ed.w), &t)) {
-      const unsigned long long key = hit_key(e, t, 16 + q, 0);
+      const unsigned long long key = hit_key(t, 16 + q, 0);
       best = key < best ? key : best;
     }
   }
@@ -159,7 +161,7 @@ ORCA_HD unsigned long long obstacle_hits(const AgentScan& A, float2 e, float2 ew
 }
 
 // Phase B: nearest hit of the ray on the polygon around `rel` (agent neighbor `item` < 16) as a key
-// (distance bits << 32 | item << 5 | edge), or kObsNoHit.  `enabled` = false: no work, the lane
+// (ray-parameter bits << 32 | item << 5 | edge), or kObsNoHit.  `enabled` = false: no work, the lane
 // only keeps its warp company.
 //
 // `drop_exit` (kernel only; the host twin tests every candidate edge): the caller guarantees that
@@ -207,26 +209,16 @@ ORCA_HD unsigned long long pair_test(const float2* poly, int C, float2 rel, floa
     edges &= edges - 1u;
     float t;
     if (ray_hit_t(ew, add(poly[m - 1], rel), add(poly[m < C ? m : 0], rel), &t)) {
-      const unsigned long long key = hit_key(e, t, item, m);
+      const unsigned long long key = hit_key(t, item, m);
       best = key < best ? key : best;
     }
   }
   return best;
 }
 
-// The ray parameter of a segment ray_hit_t has already accepted: the same two expressions, no tests.
-ORCA_HD float ray_t_of_hit(float2 e, float2 p2, float2 p3) {
-  const float bx = p3.x - p2.x, by = p3.y - p2.y;
-  const float denom = e.x * by - bx * e.y;
-  const float cx = -p2.x, cy = -p2.y;
-  const float t_num = bx * cy - by * cx;
-  return t_num / denom;
-}
-
-// Phase C: the observation row entry of a ray whose winner is edge m of the polygon around `rel`
-// (neighbor velocity nv, rotated into the agent's frame) / obstacle edge `ed`.
-ORCA_HD float4 ray_result_polygon(const float2* poly, int C, float2 rel, float2 nv, float c, float s, float2 e, float2 ew, int m) {
-  const float t = ray_t_of_hit(ew, add(poly[m - 1], rel), add(poly[m < C ? m : 0], rel));
+// Phase C: the observation row entry of a ray from its winning key: hit point = t * ray_end in the
+// agent's frame; a polygon hit also reports the neighbor's velocity nv rotated into that frame.
+ORCA_HD float4 ray_result_polygon(float t, float2 nv, float c, float s, float2 e) {
   float4 out;
   out.x = t * e.x;
   out.y = t * e.y;
@@ -234,8 +226,7 @@ ORCA_HD float4 ray_result_polygon(const float2* poly, int C, float2 rel, float2 
   out.w = s * nv.x + c * nv.y;
   return out;
 }
-ORCA_HD float4 ray_result_edge(float4 ed, float2 e, float2 ew) {
-  const float t = ray_t_of_hit(ew, v2(ed.x, ed.y), v2(ed.z, ed.w));
+ORCA_HD float4 ray_result_edge(float t, float2 e) {
   float4 out;
   out.x = t * e.x;
   out.y = t * e.y;
@@ -243,13 +234,13 @@ ORCA_HD float4 ray_result_edge(float4 ed, float2 e, float2 ew) {
   out.w = 0.f;
   return out;
 }
-ORCA_HD float4 ray_result(const ObsArgs& a, const AgentScan& A, float2 e, float2 ew, unsigned long long key) {
+ORCA_HD float4 ray_result(const ObsArgs& a, const AgentScan& A, float2 e, unsigned long long key) {
   float4 out;
   out.x = out.y = out.z = out.w = 0.f;
   if (key == kObsNoHit) return out;
-  const int item = (int)((key >> 5) & 31ull), m = (int)(key & 31ull);
-  if (item < 16) return ray_result_polygon(a.poly, a.C, A.rel[item], a.vel[A.nbr[item]], A.c, A.s, e, ew, m);
-  return ray_result_edge(A.edge[item - 16], e, ew);
+  const int item = (int)((key >> 5) & 31ull);
+  if (item < 16) return ray_result_polygon(hit_key_t(key), a.vel[A.nbr[item]], A.c, A.s, e);
+  return ray_result_edge(hit_key_t(key), e);
 }
 
 // All phases for one ray, serially (host twin of the kernel; same functions, same order).
@@ -278,7 +269,7 @@ ORCA_HD float4 observe_ray(const ObsArgs& a, int g, int ray) {
       best = key < best ? key : best;
     }
   }
-  return ray_result(a, A, e, ew, best);
+  return ray_result(a, A, e, best);
 }
 
 #if defined(__CUDACC__)
@@ -300,7 +291,7 @@ ORCA_HD float4 observe_ray(const ObsArgs& a, int g, int ray) {
 //   queue    the marked (agent, ray, neighbor) pairs -- 5 to 10 per agent -- go to a warp-private
 //            queue; whenever 32 are pending the warp runs the exact polygon test on them with every
 //            lane live (pair_test, the function the host twin calls; exit edges skipped, see there),
-//            and a hit lowers the ray's 64-bit key (distance bits, item, edge) with a shared-memory
+//            and a hit lowers the ray's 64-bit key (ray-parameter bits, item, edge) with a shared-memory
 //            atomicMin, which also encodes the reference's first-segment-wins order.
 //   rows     after the last pass the rest of the queue is drained and the rows are written (float4
 //            per ray, 128 contiguous bytes per agent and store).
@@ -439,7 +430,7 @@ __global__ void __launch_bounds__(kObsThreads, ORCA_OBS_BLOCKS_PER_SM) observe_k
   if (threadIdx.x < a.C) s_poly[threadIdx.x] = a.poly[threadIdx.x];
   __syncthreads();
 
-  const int total = a.E * a.N;
+  [[maybe_unused]] const int total = a.E * a.N;  // ORCA_DCHECK only
   const long long chunk = (long long)blockIdx.x * kObsWarps + warp;
   if (chunk > p.last_chunk) return;
   const int g_first = (int)(chunk * p.A);
@@ -558,11 +549,11 @@ __global__ void __launch_bounds__(kObsThreads, ORCA_OBS_BLOCKS_PER_SM) observe_k
           }
           float t;
           if (ray_hit_t(ew0, v2(ed.x, ed.y), v2(ed.z, ed.w), &t)) {
-            const unsigned long long key = hit_key(e0, t, 16 + q, 0);
+            const unsigned long long key = hit_key(t, 16 + q, 0);
             b0 = key < b0 ? key : b0;
           }
           if (PAIRED && ray_hit_t(ew1, v2(ed.x, ed.y), v2(ed.z, ed.w), &t)) {
-            const unsigned long long key = hit_key(e1, t, 16 + q, 0);
+            const unsigned long long key = hit_key(t, 16 + q, 0);
             b1 = key < b1 ? key : b1;
           }
         }
@@ -609,21 +600,11 @@ __global__ void __launch_bounds__(kObsThreads, ORCA_OBS_BLOCKS_PER_SM) observe_k
         if (key != kObsNoHit) {
           const float4 rt = s_ray[ray];
           const float2 e = v2(rt.x, rt.y);
-          const float2 ew = ray_world(cs.x, cs.y, e);
-          const int item = (int)((key >> 5) & 31ull), m = (int)(key & 31ull);
+          const int item = (int)((key >> 5) & 31ull);
           if (item < 16) {
-            const int slot = (ac << p.logKP) + item;
-            out = ray_result_polygon(s_poly, a.C, M.rel[slot], a.vel[M.nbr[slot]], cs.x, cs.y, e, ew, m);
+            out = ray_result_polygon(hit_key_t(key), a.vel[M.nbr[(ac << p.logKP) + item]], cs.x, cs.y, e);
           } else {
-            const int q = item - 16;
-            float4 ed;
-            if (q < kObsEdgeSlots) {
-              ed = M.edge[ac * kObsEdgeSlots + q];
-            } else {
-              const size_t voff = a.vert_stride ? (size_t)obs_env_of(g, a.N, p.n_magic) * a.vert_stride : 0;
-              ed = obs_edge(a, voff, g, q, M.pos[ac]);
-            }
-            out = ray_result_edge(ed, e, ew);
+            out = ray_result_edge(hit_key_t(key), e);
           }
         }
         a.obs[(size_t)g * a.R + ray] = out;
