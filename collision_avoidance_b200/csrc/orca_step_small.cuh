@@ -1076,7 +1076,7 @@ __device__ __forceinline__ void build_tile_grid(const StepArgs& a, void* area, c
 // Measured (config 2, 214 us at 3 blocks): 2 blocks 272 us, 1 block 480 us -- resident warps are what hides
 // the dependent-instruction latency of the LP chains.
 template <int K, bool KFULL, int POLICY, int OL = ORCA_MAX_OBST_LINES>
-__global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, (OL <= 2 ? 4 : ORCA_STEP_MIN_BLOCKS)) step_small_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(ORCA_STEP_MAX_THREADS, ((OL <= 2 || K <= 5) ? 4 : ORCA_STEP_MIN_BLOCKS)) step_small_kernel(const StepArgs a) {
   extern __shared__ float4 smem4[];
   const int tpb = blockDim.x;
   // [pos | vel] tile: 2 * tpb float2 = tpb float4 ; lines: (K + OL) * tpb float4 ;
