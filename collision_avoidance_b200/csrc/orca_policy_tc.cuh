@@ -40,13 +40,20 @@
 
 namespace orca {
 
+#ifndef ORCA_TC_GROUPS
+#define ORCA_TC_GROUPS 4  // dev A/B: 2 = the round-1 pipeline (a_hi and a_lo resident, next row prefetched into registers)
+#endif
 constexpr int kTcTile = 128;     // rows per CTA tile = MMA M = TMEM lanes
-constexpr int kTcGroups = 2;     // independent 128-thread pipelines per CTA
+constexpr int kTcGroups = ORCA_TC_GROUPS;  // independent 128-thread pipelines per CTA
+constexpr bool kTcTwoPhase = kTcGroups > 2;  // one A tile per group, a_lo and a_hi take turns in it
 constexpr int kTcThreads = 128 * kTcGroups;
 constexpr int kTcN = 64;         // MMA N = hidden width
 constexpr int kTcK = 64;         // reduction length of both GEMMs
-constexpr int kTcAccCols = 3 * kTcN;         // per group: a_hi | a_lo | accumulator, 64 columns each
+// per group: a_hi | a_lo | accumulator, 64 columns each; two-phase: A | accumulator
+constexpr int kTcAccCols = (kTcTwoPhase ? 2 : 3) * kTcN;
+constexpr int kTcDCol = kTcAccCols - kTcN;   // first accumulator column of a group
 constexpr int kTcTmemCols = 512;             // power of two >= kTcGroups * kTcAccCols
+static_assert(kTcGroups * kTcAccCols <= kTcTmemCols, "tensor memory has 512 columns");
 
 // byte sizes / strides of the K-major SWIZZLE_NONE operand tiles: a core matrix is 8 rows x 16 B
 // (4 tf32), stored as 128 contiguous bytes; core matrices of consecutive 8-row groups follow each
@@ -55,9 +62,16 @@ constexpr uint32_t kTcSbo = 128;
 constexpr uint32_t kTcLboB = (kTcN / 8) * 128;     // 1024
 constexpr uint32_t kTcBytesB = kTcN * kTcK * 4;     // 16 KB
 
+// Observation rows are staged per WARP (32 rows = 8 KB of contiguous global memory) with coalesced
+// 16-byte cp.async into rows of 68 floats: thread r then reads row r with 16 conflict-free LDS.128
+// (68 words per row: eight lanes cover the 32 banks).  One buffer per warp: a tile's rows are in
+// registers before the next tile's copies are issued.
+constexpr int kTcStagePitch = kTcK + 4;                       // floats per staged row
+constexpr int kTcStageWarpBytes = 32 * kTcStagePitch * 4;     // 8,704
 inline size_t mlp_tc_smem_bytes() {
-  return 4 * (size_t)kTcBytesB + sizeof(float) * (kMlpHidden * kMlpMaxOut + 2 * kMlpHidden + kMlpMaxOut) +
-         64 /* mbarrier + tmem base */ + 1024 /* alignment slack */;
+  return 4 * (size_t)kTcBytesB + (size_t)(kTcThreads / 32) * kTcStageWarpBytes +
+         sizeof(float) * (kMlpHidden * kMlpMaxOut + 2 * kMlpHidden + kMlpMaxOut) + 64 /* mbarrier + tmem base */ +
+         1024 /* alignment slack */;
 }
 
 #if defined(__CUDACC__)
@@ -124,6 +138,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 __device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;\n" ::"r"(group + 1) : "memory"); }
+// 16 bytes global -> shared without passing through registers; src_bytes = 0 fills with zeros
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -171,10 +191,44 @@ __device__ __forceinline__ void store_row_split(uint32_t lane_base, const float*
   tmem_st_wait();
 }
 
+// two-phase pipeline: the a_lo (part 0) or a_hi (part 1) half of this thread's row -> its TMEM lane of
+// the group's single A tile (columns [0, 64))
+template <int PART>
+__device__ __forceinline__ void store_row_part(uint32_t lane_base, const float* v) {
+#pragma unroll
+  for (int q = 0; q < kTcK / 16; ++q) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float hi = tf32_hi(v[16 * q + i]);
+      x[i] = PART ? hi : v[16 * q + i] - hi;
+    }
+    tmem_st16(lane_base + (uint32_t)(16 * q), x);
+  }
+  tmem_st_wait();
+}
+// phase 0: D = a_lo . w_hi (the small terms first, 8 MMAs); phase 1: D += a_hi . w_lo + a_hi . w_hi (16 MMAs)
+template <int PART>
+__device__ __forceinline__ void issue_gemm_part(uint32_t tmem_group, uint32_t b_hi, uint32_t b_lo, uint32_t idesc) {
+  const uint32_t d = tmem_group + (uint32_t)kTcDCol;
+#pragma unroll
+  for (int ks = 0; ks < kTcK / 8; ++ks) {
+    const uint32_t at = tmem_group + (uint32_t)(8 * ks);
+    const uint64_t dbh = make_desc(b_hi + (uint32_t)ks * 2u * kTcLboB, kTcLboB, kTcSbo);
+    if (PART == 0) {
+      mma_tf32_ts(d, at, dbh, idesc, ks > 0 ? 1u : 0u);
+    } else {
+      const uint64_t dbl = make_desc(b_lo + (uint32_t)ks * 2u * kTcLboB, kTcLboB, kTcSbo);
+      mma_tf32_ts(d, at, dbl, idesc, 1u);
+      mma_tf32_ts(d, at, dbh, idesc, 1u);
+    }
+  }
+}
+
 // D[tmem] = A . B over K = 64 with the 3xTF32 split: 8 k-steps x 3 MMAs (issued by ONE thread).
 // tmem_group: first column of the group (a_hi | a_lo | D), lane 0.
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_group, uint32_t b_hi, uint32_t b_lo, uint32_t idesc) {
-  const uint32_t d = tmem_group + 2u * (uint32_t)kTcN;
+  const uint32_t d = tmem_group + (uint32_t)kTcDCol;
 #pragma unroll
   for (int ks = 0; ks < kTcK / 8; ++ks) {  // one MMA consumes K = 8 tf32: 8 TMEM columns of A, two 16-byte chunks of B
     const uint32_t ah = tmem_group + (uint32_t)(8 * ks), al = ah + (uint32_t)kTcN;
@@ -191,19 +245,39 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_group, uint32_t b_hi, u
 __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpArgs a) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = tid >> 7, gtid = tid & 127;  // pipeline of this thread, row of the tile / TMEM lane
   uint8_t* w1_hi = base;
   uint8_t* w1_lo = w1_hi + kTcBytesB;
   uint8_t* w2_hi = w1_lo + kTcBytesB;
   uint8_t* w2_lo = w2_hi + kTcBytesB;
-  float* w3 = reinterpret_cast<float*>(w2_lo + kTcBytesB);  // [64][n_out]
+  uint8_t* stage = w2_lo + kTcBytesB + (size_t)warp * kTcStageWarpBytes;  // this warp's 32 staged rows
+  float* w3 = reinterpret_cast<float*>(w2_lo + kTcBytesB + (size_t)(kTcThreads / 32) * kTcStageWarpBytes);  // [n_out][64]
   float* b1 = w3 + kMlpHidden * kMlpMaxOut;
   float* b2 = b1 + kMlpHidden;
   float* b3 = b2 + kMlpHidden;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b3 + kMlpMaxOut);  // one per group
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTcGroups);
   uint64_t* bar = bars + group;
+
+  const long long tiles = (a.rows + kTcTile - 1) / kTcTile;
+  const long long first_tile = (long long)blockIdx.x * kTcGroups + group, tile_step = (long long)gridDim.x * kTcGroups;
+  // coalesced copy of this warp's 32 rows of `tile` (512 chunks of 16 bytes, 16 per lane) into its buffer
+  const uint32_t s_stage = tc::smem_u32(stage);
+  auto stage_rows = [&](long long tile) {
+    if (tile < tiles) {
+      const long long row0 = tile * kTcTile + (gtid & ~31);
+      const float* src = a.obs + row0 * kMlpIn;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = i * 32 + lane, r = c >> 4, q = c & 15;
+        const bool have = row0 + r < a.rows;
+        tc::cp_async16(s_stage + (uint32_t)(r * kTcStagePitch * 4 + q * 16), have ? src + c * 4 : a.obs, have ? 16u : 0u);
+      }
+    }
+    tc::cp_async_commit();
+  };
+  stage_rows(first_tile);  // in flight during the set-up
 
   // ---- one-time setup: weights (split, K-major core-matrix layout), barrier, TMEM ----
   for (int i = tid; i < kTcK * kTcN; i += kTcThreads) {
@@ -216,7 +290,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
     *reinterpret_cast<float*>(w2_hi + off) = h2;
     *reinterpret_cast<float*>(w2_lo + off) = x2 - h2;
   }
-  for (int i = tid; i < kMlpHidden * a.n_out; i += kTcThreads) w3[i] = __ldg(a.w3 + i);
+  // head weights transposed to [o][n]: the head reads them as float4 over n
+  for (int i = tid; i < kMlpHidden * a.n_out; i += kTcThreads) w3[(i % a.n_out) * kMlpHidden + i / a.n_out] = __ldg(a.w3 + i);
   if (tid < kMlpHidden) {
     b1[tid] = __ldg(a.b1 + tid);
     b2[tid] = __ldg(a.b2 + tid);
@@ -243,93 +318,97 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
   const uint32_t s_w2_hi = tc::smem_u32(w2_hi), s_w2_lo = tc::smem_u32(w2_lo);
   const uint32_t s_bar = tc::smem_u32(bar);
   uint32_t parity = 0;
-
-  const long long tiles = (a.rows + kTcTile - 1) / kTcTile;
   float v[kTcK];  // this thread's row: observation, then h1, then h2
 
-  const long long first_tile = (long long)blockIdx.x * kTcGroups + group, tile_step = (long long)gridDim.x * kTcGroups;
-  // prefetch the first tile's row
-  {
-    const long long row = first_tile * kTcTile + gtid;
-#pragma unroll
-    for (int c = 0; c < kTcK / 4; ++c) {
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (first_tile < tiles && row < a.rows) x = __ldg(reinterpret_cast<const float4*>(a.obs + row * kMlpIn) + c);
-      v[4 * c + 0] = x.x;
-      v[4 * c + 1] = x.y;
-      v[4 * c + 2] = x.z;
-      v[4 * c + 3] = x.w;
-    }
-  }
-
-  for (long long tile = first_tile; tile < tiles; tile += tile_step) {
-    const long long row = tile * kTcTile + gtid;
-
-    // ---- GEMM 1: obs . W1 ----
-    tc::store_row_split(lane_base, v);
-    tc::fence_before_sync();
-    tc::group_sync(group);
-    if (gtid == 0) {
+  // one layer: v (this thread's row of A) -> v (its row of A . W), 3xTF32
+  auto run_layer = [&](uint32_t s_hi, uint32_t s_lo) {
+    if constexpr (kTcTwoPhase) {
+      // a_lo -> the A tile, 8 MMAs, wait (the MMAs have read the tile), a_hi -> the same tile, 16 MMAs
+      tc::store_row_part<0>(lane_base, v);
+      tc::fence_before_sync();
+      tc::group_sync(group);
+      if (gtid == 0) {
+        tc::fence_after_sync();
+        tc::issue_gemm_part<0>(tmem_base, s_hi, s_lo, idesc);
+        tc::mma_commit(s_bar);
+      }
+      tc::mbar_wait(s_bar, parity);
+      parity ^= 1u;
       tc::fence_after_sync();
-      tc::issue_gemm(tmem_base, s_w1_hi, s_w1_lo, idesc);
-      tc::mma_commit(s_bar);
-    }
-    // while the tensor core works: fetch the next tile's row of observations
-    float nxt[kTcK];
-    {
-      const long long nrow = (tile + tile_step) * kTcTile + gtid;
-      const bool have = (tile + tile_step) < tiles && nrow < a.rows;
-#pragma unroll
-      for (int c = 0; c < kTcK / 4; ++c) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-#if !defined(ORCA_TC_DEV_NO_LOAD)  // dev A/B: no observation traffic
-        if (have) x = __ldg(reinterpret_cast<const float4*>(a.obs + nrow * kMlpIn) + c);
-#endif
-        nxt[4 * c + 0] = x.x;
-        nxt[4 * c + 1] = x.y;
-        nxt[4 * c + 2] = x.z;
-        nxt[4 * c + 3] = x.w;
+      tc::store_row_part<1>(lane_base, v);
+      tc::fence_before_sync();
+      tc::group_sync(group);
+      if (gtid == 0) {
+        tc::fence_after_sync();
+        tc::issue_gemm_part<1>(tmem_base, s_hi, s_lo, idesc);
+        tc::mma_commit(s_bar);
+      }
+    } else {
+      tc::store_row_split(lane_base, v);
+      tc::fence_before_sync();
+      tc::group_sync(group);
+      if (gtid == 0) {
+        tc::fence_after_sync();
+        tc::issue_gemm(tmem_base, s_hi, s_lo, idesc);
+        tc::mma_commit(s_bar);
       }
     }
     tc::mbar_wait(s_bar, parity);
     parity ^= 1u;
     tc::fence_after_sync();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tc::tmem_ld16(lane_base + (uint32_t)(2 * kTcN + 16 * q), v + 16 * q);
+    for (int q = 0; q < 4; ++q) tc::tmem_ld16(lane_base + (uint32_t)(kTcDCol + 16 * q), v + 16 * q);
     tc::tmem_ld_wait();
+  };
+  auto bias_relu = [&](const float* b) {
 #pragma unroll
-    for (int n = 0; n < kTcN; ++n) v[n] = fmaxf(v[n] + b1[n], 0.f);
-
-    // ---- GEMM 2: h1 . W2 (the A columns are free: GEMM 1 has completed) ----
-    tc::store_row_split(lane_base, v);
-    tc::fence_before_sync();
-    tc::group_sync(group);
-    if (gtid == 0) {
-      tc::fence_after_sync();
-      tc::issue_gemm(tmem_base, s_w2_hi, s_w2_lo, idesc);
-      tc::mma_commit(s_bar);
+    for (int n = 0; n < kTcN; n += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(b + n);  // broadcast
+      v[n + 0] = fmaxf(v[n + 0] + bb.x, 0.f);
+      v[n + 1] = fmaxf(v[n + 1] + bb.y, 0.f);
+      v[n + 2] = fmaxf(v[n + 2] + bb.z, 0.f);
+      v[n + 3] = fmaxf(v[n + 3] + bb.w, 0.f);
     }
-    tc::mbar_wait(s_bar, parity);
-    parity ^= 1u;
-    tc::fence_after_sync();
+  };
+
+  for (long long tile = first_tile; tile < tiles; tile += tile_step) {
+    const long long row = tile * kTcTile + gtid;
+    // this thread's row out of the warp's staging buffer, then the next tile's copies into it
+    tc::cp_async_wait_all();
+    __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tc::tmem_ld16(lane_base + (uint32_t)(2 * kTcN + 16 * q), v + 16 * q);
-    tc::tmem_ld_wait();
-#pragma unroll
-    for (int n = 0; n < kTcN; ++n) v[n] = fmaxf(v[n] + b2[n], 0.f);
+    for (int c = 0; c < kTcK / 4; ++c) {
+      const float4 x = *reinterpret_cast<const float4*>(stage + (size_t)lane * (kTcStagePitch * 4) + c * 16);
+      v[4 * c + 0] = x.x;
+      v[4 * c + 1] = x.y;
+      v[4 * c + 2] = x.z;
+      v[4 * c + 3] = x.w;
+    }
+    __syncwarp();
+    stage_rows(tile + tile_step);
+
+    run_layer(s_w1_hi, s_w1_lo);
+    bias_relu(b1);
+    run_layer(s_w2_hi, s_w2_lo);
+    bias_relu(b2);
 
     // ---- head: 64 -> n_out on the registers ----
     if (row < a.rows) {
       for (int o = 0; o < a.n_out; ++o) {
         float acc = b3[o];
 #pragma unroll
-        for (int n = 0; n < kTcN; ++n) acc = fmaf(v[n], w3[n * a.n_out + o], acc);
+        for (int n = 0; n < kTcN; n += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(w3 + o * kMlpHidden + n);  // broadcast
+          acc = fmaf(v[n + 0], w.x, acc);
+          acc = fmaf(v[n + 1], w.y, acc);
+          acc = fmaf(v[n + 2], w.z, acc);
+          acc = fmaf(v[n + 3], w.w, acc);
+        }
         a.out[row * a.n_out + o] = acc;
       }
     }
-#pragma unroll
-    for (int n = 0; n < kTcK; ++n) v[n] = nxt[n];
   }
+  tc::cp_async_wait_all();
 
   // ---- teardown ----
   tc::fence_before_sync();
