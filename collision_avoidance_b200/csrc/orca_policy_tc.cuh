@@ -144,6 +144,18 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// one lane of the (converged) warp: the form the compiler recognises for single-thread tcgen05 issue
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0u;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -210,6 +222,9 @@ __device__ __forceinline__ void store_row_part(uint32_t lane_base, const float* 
 // phase 0: D = a_lo . w_hi (the small terms first, 8 MMAs); phase 1: D += a_hi . w_lo + a_hi . w_hi (16 MMAs)
 template <int PART>
 __device__ __forceinline__ void issue_gemm_part(uint32_t tmem_group, uint32_t b_hi, uint32_t b_lo, uint32_t idesc) {
+#if defined(ORCA_TC_DEV_NO_MMA)  // dev A/B (wrong results): no tensor work, the commit arrives at once
+  return;
+#endif
   const uint32_t d = tmem_group + (uint32_t)kTcDCol;
 #pragma unroll
   for (int ks = 0; ks < kTcK / 8; ++ks) {
@@ -245,8 +260,14 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_group, uint32_t b_hi, u
 __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpArgs a) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int group = tid >> 7, gtid = tid & 127;  // pipeline of this thread, row of the tile / TMEM lane
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp index through a shuffle: the compiler then knows that everything derived from it (tensor-memory
+  // addresses, descriptors, barrier addresses) is warp-uniform and issues the MMAs from uniform registers
+  // directly instead of wrapping each one in a loop over the distinct operand values of the warp
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int group = warp >> 2, gtid = tid & 127;  // pipeline of this thread, row of the tile / TMEM lane
+  // the issuing thread of group g is lane 0 of the group's warp g: the four issuers sit on four different schedulers
+  const bool issuer_warp = (warp & 3) == (group & 3);
   uint8_t* w1_hi = base;
   uint8_t* w1_lo = w1_hi + kTcBytesB;
   uint8_t* w2_hi = w1_lo + kTcBytesB;
@@ -269,11 +290,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
       const long long row0 = tile * kTcTile + (gtid & ~31);
       const float* src = a.obs + row0 * kMlpIn;
 #pragma unroll
+#if !defined(ORCA_TC_DEV_NO_LOAD)  // dev A/B (wrong results): no observation traffic
       for (int i = 0; i < 16; ++i) {
         const int c = i * 32 + lane, r = c >> 4, q = c & 15;
         const bool have = row0 + r < a.rows;
         tc::cp_async16(s_stage + (uint32_t)(r * kTcStagePitch * 4 + q * 16), have ? src + c * 4 : a.obs, have ? 16u : 0u);
       }
+#endif
     }
     tc::cp_async_commit();
   };
@@ -327,7 +350,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
       tc::store_row_part<0>(lane_base, v);
       tc::fence_before_sync();
       tc::group_sync(group);
-      if (gtid == 0) {
+      if (issuer_warp && tc::elect_one()) {
         tc::fence_after_sync();
         tc::issue_gemm_part<0>(tmem_base, s_hi, s_lo, idesc);
         tc::mma_commit(s_bar);
@@ -338,7 +361,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
       tc::store_row_part<1>(lane_base, v);
       tc::fence_before_sync();
       tc::group_sync(group);
-      if (gtid == 0) {
+      if (issuer_warp && tc::elect_one()) {
         tc::fence_after_sync();
         tc::issue_gemm_part<1>(tmem_base, s_hi, s_lo, idesc);
         tc::mma_commit(s_bar);
@@ -347,7 +370,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
       tc::store_row_split(lane_base, v);
       tc::fence_before_sync();
       tc::group_sync(group);
-      if (gtid == 0) {
+      if (issuer_warp && tc::elect_one()) {
         tc::fence_after_sync();
         tc::issue_gemm(tmem_base, s_hi, s_lo, idesc);
         tc::mma_commit(s_bar);
