@@ -14,23 +14,31 @@
 // accumulated in FP32 in TMEM: error ~2^-21 relative per product, the same order as FP32 itself.
 // Tensor-core time triples and still hides behind the HBM read.
 //
-// One CTA = two independent groups of 128 threads; a group = 128 agents (one TMEM lane each),
-// persistent over row tiles.  The groups share the weight tiles and nothing else (own A tiles, own
-// accumulator columns, own mbarrier, named barriers): while one waits for its MMAs the other runs
-// its epilogue, so the four schedulers of the SM always have a warp with work.  Per group:
+// One CTA = FOUR independent groups of 128 threads; a group = 128 agents (one TMEM lane each),
+// persistent over row tiles.  The groups share the weight tiles and nothing else (own A tile, own
+// accumulator columns, own mbarrier, named barriers): while one waits for its MMAs the others run
+// their epilogues.  Per group:
 //   - weights (B operands): split once per CTA into K-major SWIZZLE_NONE core-matrix layout in
 //     shared memory, 4 x 16 KB;
+//   - observation rows: a warp stages ITS 32 rows (8 KB of contiguous global memory) with coalesced
+//     16-byte cp.async into a padded buffer and thread r reads row r back with conflict-free
+//     LDS.128.  (Per-thread row loads -- 32 lines per warp-level load -- kept the L1 data pipe at
+//     63-68 % of its wavefront peak: that, not HBM and not the tensor pipe, bound the first version.)
+//     The next tile's copies are issued as soon as this tile's rows are in registers;
 //   - the A operand lives in TENSOR MEMORY (tcgen05.mma with A from TMEM): row r of the tile is
-//     TMEM lane r, which is exactly what thread r owns -- it splits its own observation row
-//     (prefetched into registers during the previous tile's MMAs) and writes a_hi / a_lo with
+//     TMEM lane r, which is exactly what thread r owns -- it splits its own row and writes it with
 //     tcgen05.st, no shared-memory staging, no proxy fence.  With N = 64 an MMA that fetches A from
 //     shared memory is bound by that fetch (4 KB of A + 2 KB of B per 128x64x8 MMA, measured 53 ns
-//     each); from TMEM only the 2 KB of B cross the shared-memory port;
-//   - one thread issues 8 k-steps x 3 tcgen05.mma (M = 128, N = 64, K = 8) and commits to an
+//     each); from TMEM only the 2 KB of B cross the shared-memory port.  A group has ONE A tile
+//     (64 columns): a_lo goes in first (8 MMAs with w_hi), then a_hi (16 MMAs with w_lo and w_hi);
+//   - an elected lane of a converged warp issues the MMAs (elect.sync: issued under `lane == 0`
+//     ptxas wraps every tcgen05.mma in a loop over the warp's operand values) and commits to an
 //     mbarrier; every thread then pulls ITS row of the accumulator with tcgen05.ld, adds the bias,
 //     applies ReLU, splits again and stores the row back as the A operand of the second GEMM; the
 //     64 -> out head is a handful of FMAs on the registers that tcgen05.ld delivered.
-// Tensor memory per group: a_hi 64 + a_lo 64 + accumulator 64 columns; shared memory ~67 KB.
+// Tensor memory per group: A 64 + accumulator 64 columns (4 x 128 = all 512); 128 registers per
+// thread; shared memory ~205 KB (64 KB weights + 16 x 8.5 KB staging).  -DORCA_TC_GROUPS=2 builds
+// the round-1 arrangement (a_hi and a_lo resident, 192 columns per group) for A/B runs.
 #pragma once
 
 #include <cuda_runtime.h>
