@@ -588,7 +588,20 @@ ORCA_HD bool agent_front(const StepArgs& a, const int env, const int g, const in
     a.nbr_cnt[g] = cnt;
   }
   if (a.onbr_idx != nullptr) {
-    for (int s = 0; s < ORCA_MAX_OBST_NEIGHBORS; ++s) a.onbr_idx[(size_t)g * ORCA_MAX_OBST_NEIGHBORS + s] = (s < ocnt) ? oid[s] : -1;
+    int* row = a.onbr_idx + (size_t)g * ORCA_MAX_OBST_NEIGHBORS;
+    if ((reinterpret_cast<uintptr_t>(a.onbr_idx) & 15u) == 0u) {  // uniform; 16-byte stores: a quarter of the store wavefronts
+#pragma unroll
+      for (int s = 0; s < ORCA_MAX_OBST_NEIGHBORS; s += 4) {
+        int4 w;
+        w.x = (s + 0 < ocnt) ? oid[s + 0] : -1;
+        w.y = (s + 1 < ocnt) ? oid[s + 1] : -1;
+        w.z = (s + 2 < ocnt) ? oid[s + 2] : -1;
+        w.w = (s + 3 < ocnt) ? oid[s + 3] : -1;
+        *reinterpret_cast<int4*>(row + s) = w;
+      }
+    } else {
+      for (int s = 0; s < ORCA_MAX_OBST_NEIGHBORS; ++s) row[s] = (s < ocnt) ? oid[s] : -1;
+    }
     a.onbr_cnt[g] = ocnt;
   }
   if (a.neighbors_only) return false;
