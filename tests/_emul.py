@@ -59,7 +59,7 @@ def lib():
             # ORCA_EMUL_SANITIZE=1: AddressSanitizer + UBSan build of the library's per-agent device code
             # (run the suite with LD_PRELOAD=$(gcc -print-file-name=libasan.so); see profiles/README.md)
             san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"] if os.environ.get("ORCA_EMUL_SANITIZE") else []
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", *san,
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", *san, *os.environ.get("ORCA_EMUL_DEFINES", "").split(),
                                    "-Wno-unknown-pragmas", "-I" + os.path.join(_HERE, "host_emul"), "-o", _LIB, _SRC])
         L = ctypes.CDLL(_LIB)
         L.emul_stepargs_size.restype = c_i
