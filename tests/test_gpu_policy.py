@@ -44,6 +44,25 @@ def test_policy_mlp_matches_torch(rows, n_out, impl):
     assert float((y - (h @ pol.w3 + pol.b3)).abs().max()) <= TOL
 
 
+def test_tensor_core_kernel_over_many_tiles_per_group():
+    """The persistent loop of the tensor-core kernel: with 1,000,003 rows every 128-thread group walks
+    13-14 row tiles (staging buffer reused per tile, mbarrier parity flipping four times per tile,
+    a ragged last tile), which the small cases above never reach."""
+    import torch
+    from collision_avoidance_b200.policy import SharedMLPPolicy
+    rows = 1_000_003
+    pol = SharedMLPPolicy(_sim(), num_outputs=2, seed=11, impl="tcgen05")
+    g = torch.Generator().manual_seed(3)
+    for b in (pol.b1, pol.b2, pol.b3):
+        b.copy_(torch.randn(b.shape, generator=g) * 0.3)
+    obs = (torch.randn(rows, 64, generator=g) * 2.0).cuda()
+    y = pol(obs)
+    ref = _reference(pol, obs)
+    assert float((y - ref).abs().max()) <= TOL
+    y2 = pol(obs)   # and it is deterministic
+    assert torch.equal(y, y2)
+
+
 def test_tensor_core_kernel_is_fp32_accurate_not_tf32_accurate():
     """The 3xTF32 split must buy FP32-level accuracy: a plain TF32 product would be off by ~1e-3
     on these O(10) pre-activations; the kernel has to stay within 2e-5 of float64."""
