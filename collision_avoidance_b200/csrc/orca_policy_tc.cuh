@@ -239,7 +239,7 @@ __device__ __forceinline__ void issue_gemm_part(uint32_t tmem_group, uint32_t b_
     const uint32_t at = tmem_group + (uint32_t)(8 * ks);
     const uint64_t dbh = make_desc(b_hi + (uint32_t)ks * 2u * kTcLboB, kTcLboB, kTcSbo);
     if (PART == 0) {
-      mma_tf32_ts(d, at, dbh, idesc, ks > 0 ? 1u : 0u);
+      mma_tf32_ts(d, at, dbh, idesc, 1u);  // the accumulator starts from the bias row (run_layer)
     } else {
       const uint64_t dbl = make_desc(b_lo + (uint32_t)ks * 2u * kTcLboB, kTcLboB, kTcSbo);
       mma_tf32_ts(d, at, dbl, idesc, 1u);
@@ -293,12 +293,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
   const long long first_tile = (long long)blockIdx.x * kTcGroups + group, tile_step = (long long)gridDim.x * kTcGroups;
   // coalesced copy of this warp's 32 rows of `tile` (512 chunks of 16 bytes, 16 per lane) into its buffer
   const uint32_t s_stage = tc::smem_u32(stage);
+  const uint32_t s_stage_lane = s_stage + (uint32_t)((lane >> 4) * kTcStagePitch * 4 + (lane & 15) * 16);
   auto stage_rows = [&](long long tile) {
     if (tile < tiles) {
       const long long row0 = tile * kTcTile + (gtid & ~31);
       const float* src = a.obs + row0 * kMlpIn;
-#pragma unroll
 #if !defined(ORCA_TC_DEV_NO_LOAD)  // dev A/B (wrong results): no observation traffic
+      if (row0 + 32 <= a.rows) {  // warp-uniform: all 32 rows exist -- constant offsets from one address pair
+        const float* src_lane = src + lane * 4;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tc::cp_async16(s_stage_lane + (uint32_t)(i * 2 * kTcStagePitch * 4), src_lane + i * 128, 16u);
+      } else
+#pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int c = i * 32 + lane, r = c >> 4, q = c & 15;
         const bool have = row0 + r < a.rows;
@@ -352,8 +358,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
   float v[kTcK];  // this thread's row: observation, then h1, then h2
 
   // one layer: v (this thread's row of A) -> v (its row of A . W), 3xTF32
-  auto run_layer = [&](uint32_t s_hi, uint32_t s_lo) {
+  auto run_layer = [&](uint32_t s_hi, uint32_t s_lo, const float* bias) {
     if constexpr (kTcTwoPhase) {
+      // the bias enters through the accumulator: every thread writes the bias row into its lane of D
+      // (free since the previous layer was read out) and all MMAs accumulate -- 16 LDS.128 + 4 tcgen05.st
+      // instead of 64 additions after the read-out
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float bq[16];
+#pragma unroll
+        for (int n = 0; n < 16; n += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias + 16 * q + n);  // broadcast
+          bq[n + 0] = bb.x;
+          bq[n + 1] = bb.y;
+          bq[n + 2] = bb.z;
+          bq[n + 3] = bb.w;
+        }
+        tc::tmem_st16(lane_base + (uint32_t)(kTcDCol + 16 * q), bq);
+      }
       // a_lo -> the A tile, 8 MMAs, wait (the MMAs have read the tile), a_hi -> the same tile, 16 MMAs
       tc::store_row_part<0>(lane_base, v);
       tc::fence_before_sync();
@@ -392,6 +414,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
     tc::tmem_ld_wait();
   };
   auto bias_relu = [&](const float* b) {
+    if constexpr (kTcTwoPhase) {  // the bias is already in the accumulator
+#pragma unroll
+      for (int n = 0; n < kTcN; ++n) v[n] = fmaxf(v[n], 0.f);
+      return;
+    }
 #pragma unroll
     for (int n = 0; n < kTcN; n += 4) {
       const float4 bb = *reinterpret_cast<const float4*>(b + n);  // broadcast
@@ -418,9 +445,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_mlp_tc_kernel(const MlpA
     __syncwarp();
     stage_rows(tile + tile_step);
 
-    run_layer(s_w1_hi, s_w1_lo);
+    run_layer(s_w1_hi, s_w1_lo, b1);
     bias_relu(b1);
-    run_layer(s_w2_hi, s_w2_lo);
+    run_layer(s_w2_hi, s_w2_lo, b2);
     bias_relu(b2);
 
     // ---- head: 64 -> n_out on the registers ----
