@@ -317,6 +317,7 @@ struct ObsPlan {
   int last_n;
   int ccw;                     // orientation of the polygon ring
   float clear_eps;             // see pair_test
+  float far_sq;                // (longest ray, padded)^2: an obstacle edge further than this from the agent meets no ray
 };
 
 inline int obs_log2_ceil(int x) {
@@ -362,6 +363,8 @@ inline ObsPlan obs_plan(const ObsArgs& a, bool paired) {
   float len_sq = 0.f;
   for (int i = 0; i < a.R; ++i) len_sq = fmaxf(len_sq, a.ray_end[i].x * a.ray_end[i].x + a.ray_end[i].y * a.ray_end[i].y);
   p.clear_eps = fmaxf(kObsSideEps, 1e-4f * len_sq);
+  const float far = sqrtf(len_sq) * 1.001f + 1e-3f;
+  p.far_sq = far * far;
   return p;
 }
 
@@ -390,7 +393,7 @@ struct ObsWarpMem {
   float2* frame;             // [A]       (c, s)
   float2* pos;               // [A]
   int* nbr;                  // [A][KP]   global index of the neighbor
-  int* cnt;                  // [A]       agent neighbors | obstacle neighbors << 8
+  int* cnt;                  // [A]       agent neighbors | obstacle neighbors << 8 | out-of-reach bits of the staged edges << 16
   unsigned short* queue;     // [kObsQueue]  (agent of the chunk << 9) | (ray << 4) | item
 };
 
@@ -498,10 +501,15 @@ __global__ void __launch_bounds__(kObsThreads, ORCA_OBS_BLOCKS_PER_SM) observe_k
   // ---- staging, lane = (agent, obstacle-edge slot)
   for (int i = lane; i < n_chunk * kObsEdgeSlots; i += 32) {
     const int ac = i / kObsEdgeSlots, q = i % kObsEdgeSlots;
-    if (q < (M.cnt[ac] >> 8)) {
+    if (q < ((M.cnt[ac] >> 8) & 255)) {
       const int g = g_first + ac;
       const size_t voff = a.vert_stride ? (size_t)obs_env_of(g, a.N, p.n_magic) * a.vert_stride : 0;
-      M.edge[i] = obs_edge(a, voff, g, q, M.pos[ac]);
+      const float4 ed = obs_edge(a, voff, g, q, M.pos[ac]);
+      M.edge[i] = ed;
+      // The step kernel lists the edges within timeHorizonObst * maxSpeed + radius of the agent; the rays are
+      // usually much shorter (gym world: 4.4 against 1.5).  An edge whose nearest point is further away than the
+      // longest ray (padded) cannot meet any ray -- every exact test would reject it -- so the ray loop skips it.
+      if (dist_sq_point_segment(v2(ed.x, ed.y), v2(ed.z, ed.w), v2(0.f, 0.f)) > p.far_sq) atomicOr(&M.cnt[ac], 0x10000 << q);
     }
   }
   __syncwarp();
@@ -520,7 +528,8 @@ __global__ void __launch_bounds__(kObsThreads, ORCA_OBS_BLOCKS_PER_SM) observe_k
     if (valid) {
       const float2 cs = M.frame[ac];
       const int cc = M.cnt[ac];
-      const int cnt = cc & 255, ocnt = cc >> 8;
+      const int cnt = cc & 255, ocnt = (cc >> 8) & 255;
+      const unsigned far_edges = (unsigned)cc >> 16;  // staged edges (q < kObsEdgeSlots) out of every ray's reach
       const float2 e0 = v2(rt0.x, rt0.y);
       const float2 ew0 = ray_world(cs.x, cs.y, e0);
       const float2 u = v2(ew0.x * rt0.w, ew0.y * rt0.w);
@@ -540,6 +549,7 @@ __global__ void __launch_bounds__(kObsThreads, ORCA_OBS_BLOCKS_PER_SM) observe_k
         const float2 ew1 = ray_world(cs.x, cs.y, e1);
         unsigned long long b0 = kObsNoHit, b1 = kObsNoHit;
         for (int q = 0; q < ocnt; ++q) {
+          if ((far_edges >> q) & 1u) continue;
           float4 ed;
           if (q < kObsEdgeSlots) {
             ed = M.edge[ac * kObsEdgeSlots + q];
