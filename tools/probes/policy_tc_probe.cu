@@ -71,6 +71,6 @@ int main(int argc, char** argv) {
   }
   std::vector<float> o(8);
   CK(cudaMemcpy(o.data(), d_out, 32, cudaMemcpyDeviceToHost));
-  std::printf("%s us %.1f  out0 %.6f %.6f\n", argc > 2 ? argv[2] : "", total / iters * 1e3, o[0], o[1]);
+  std::printf("%s us %.1f  out0 %.9f %.9f\n", argc > 2 ? argv[2] : "", total / iters * 1e3, o[0], o[1]);
   return 0;
 }
