@@ -30,7 +30,8 @@
 //     tcgen05.st, no shared-memory staging, no proxy fence.  With N = 64 an MMA that fetches A from
 //     shared memory is bound by that fetch (4 KB of A + 2 KB of B per 128x64x8 MMA, measured 53 ns
 //     each); from TMEM only the 2 KB of B cross the shared-memory port.  A group has ONE A tile
-//     (64 columns): a_lo goes in first (8 MMAs with w_hi), then a_hi (16 MMAs with w_lo and w_hi);
+//     (64 columns): a_lo goes in first (8 MMAs with w_hi), then a_hi (16 MMAs with w_lo and w_hi) --
+//     and a_hi is the row as it is: kind::tf32 ignores the low 13 mantissa bits of its operands;
 //   - an elected lane of a converged warp issues the MMAs (elect.sync: issued under `lane == 0`
 //     ptxas wraps every tcgen05.mma in a loop over the warp's operand values) and commits to an
 //     mbarrier; every thread then pulls ITS row of the accumulator with tcgen05.ld, adds the bias,
