@@ -387,7 +387,7 @@ def run_ours(args, cfg_name, cfg):
 
         def host_region(vel_out, aux_unchanged):
             sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=1, aux_unchanged=aux_unchanged)
-            for _ in range(24):  # untimed: the library times both of its routes (direct / staged) on its first six steady calls and keeps the faster
+            for _ in range(24):  # untimed: the library times both of its routes (direct / staged) on its first ten steady calls and keeps the faster
                 sim.step_host(pos_h, vel_out, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1, aux_unchanged=aux_unchanged)
             barrier()
             per_call = []

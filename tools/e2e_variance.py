@@ -10,7 +10,7 @@ pos_h = torch.from_numpy(scn.pos.copy()).pin_memory()
 vel_h = torch.from_numpy(scn.vel.copy()).pin_memory()
 goal_h = torch.from_numpy(scn.goal.copy()).pin_memory()
 sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=True, steps=150)
-for _ in range(8):
+for _ in range(12):
     sim.step_host(pos_h, vel_h, goal_h, policy=_lib.POLICY_GOAL, upload_state=False, steps=1)
 for rep in range(8):
     ts = []
